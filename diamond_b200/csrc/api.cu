@@ -1,0 +1,681 @@
+// libdiamond_b200.so — C ABI (include/diamond_b200.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/diamond_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_tc.cuh"
+
+using namespace dmd;
+
+// ---------------------------------------------------------------------------------------------- errors / counters
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define DMD_CHECK(cond, ...) \
+  do {                       \
+    if (!(cond)) return fail(__VA_ARGS__); \
+  } while (0)
+#define DMD_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define DMD_LAUNCH_OK()                                                                 \
+  do {                                                                                  \
+    ++g_launches;                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int dmd_version(void) { return DMD_VERSION; }
+extern "C" const char* dmd_last_error(void) { return g_err.c_str(); }
+extern "C" long long dmd_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int gn_group_size(int C) {  // blocks.py:12,27: num_groups = max(1, C // 32)
+  int G = C / 32 > 1 ? C / 32 : 1;
+  return C / G;
+}
+
+// ---------------------------------------------------------------------------------------------- conv launcher
+static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* tmem_cols) {
+  DMD_CHECK(d->src0 && d->out && d->wpk, "conv: null src0/out/wpk");
+  DMD_CHECK(d->taps == 9 || d->taps == 1, "conv: taps must be 1 or 9 (got %d)", d->taps);
+  DMD_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  DMD_CHECK(d->Cin % 16 == 0 && d->Cin >= 16 && d->Cin <= kMaxCin, "conv: Cin=%d must be a multiple of 16 in [16,%d]", d->Cin, kMaxCin);
+  DMD_CHECK(d->C0 % 8 == 0 && d->C1 % 8 == 0 && d->C0 > 0 && d->C0 + d->C1 <= d->Cin, "conv: bad C0=%d C1=%d Cin=%d", d->C0, d->C1, d->Cin);
+  DMD_CHECK((d->C1 == 0) == (d->src1 == nullptr), "conv: src1/C1 mismatch");
+  DMD_CHECK(d->CoutPad % 16 == 0 && d->CoutPad >= 16 && d->CoutPad <= 128 && d->Cout <= d->CoutPad && d->Cout > 0, "conv: bad Cout=%d CoutPad=%d", d->Cout, d->CoutPad);
+  memset(p, 0, sizeof(*p));
+  p->src0 = d->src0; p->src1 = d->src1; p->C0 = d->C0; p->C1 = d->C1; p->Cin = d->Cin;
+  p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample ? 1 : 0;
+  p->H = d->upsample ? 2 * d->Hs : d->Hs;
+  p->W = d->upsample ? 2 * d->Ws : d->Ws;
+  p->taps = d->taps; p->stride = d->stride;
+  if (d->stride == 2) DMD_CHECK(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H,W");
+  p->pro = d->prologue; p->act = d->silu ? 1 : 0;
+  if (d->prologue) {
+    DMD_CHECK(d->stats0 && d->gs0 > 0 && d->C0 % d->gs0 == 0 && d->gs0 % 8 == 0, "conv: prologue needs stats0/gs0 (gs multiple of 8)");
+    if (d->C1) DMD_CHECK(d->stats1 && d->gs1 > 0 && d->C1 % d->gs1 == 0 && d->gs1 % 8 == 0, "conv: prologue needs stats1/gs1");
+    if (d->prologue == 1) DMD_CHECK(d->film != nullptr, "conv: AdaGN prologue needs film");
+    if (d->prologue == 2) DMD_CHECK(d->gamma && d->beta, "conv: GN prologue needs gamma/beta");
+    DMD_CHECK(d->upsample == 0, "conv: prologue + upsample unsupported");
+  }
+  p->st0 = d->stats0; p->st1 = d->stats1; p->gs0 = d->gs0 > 0 ? d->gs0 : 8; p->gs1 = d->gs1 > 0 ? d->gs1 : 8;
+  p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off;
+  p->gamma = d->gamma; p->beta = d->beta; p->eps = d->eps;
+  p->wpk = reinterpret_cast<const __half*>(d->wpk); p->bias = d->bias; p->Cout = d->Cout; p->CoutPad = d->CoutPad;
+  p->resid = d->residual; p->out = d->out; p->ostats = d->out_stats; p->ogs = d->out_gs > 0 ? d->out_gs : d->Cout;
+  if (d->out_stats) DMD_CHECK(d->out_gs > 0 && d->Cout % d->out_gs == 0 && d->out_gs % 16 == 0, "conv: out_gs=%d must divide Cout and be a multiple of 16", d->out_gs);
+  p->dbg = d->debug;
+  p->PW = p->W + 1; p->PH = p->H + 1;
+  const long long Q = (long long)p->B * p->PH * p->PW;
+  DMD_CHECK(Q * (p->PW > p->PH ? p->PW : p->PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
+  p->Q = (int)Q;
+  const int halo = d->taps == 9 ? p->PW + 1 : 0;
+  p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
+  DMD_CHECK((p->P + p->PH * p->PW - 1) / (p->PH * p->PW) + 1 <= kMaxImgSlots, "conv: image too small for tile (H=%d W=%d)", p->H, p->W);
+  p->dPW.init(p->PW); p->dPH.init(p->PH);
+  const ConvSmemLayout L = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc);
+  DMD_CHECK(L.total <= 227 * 1024, "conv: needs %u B shared memory (> 227 KB): W=%d Cin=%d", L.total, p->W, p->Cin);
+  *smem = L.total;
+  *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
+  return 0;
+}
+
+static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (never during stream capture)
+  static bool done = false;
+  if (done) return 0;
+  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  done = true;
+  return 0;
+}
+
+template <int kCols>
+static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
+  if (init_kernels()) return 1;
+  const int grid = (p.Q + kTileM - 1) / kTileM;
+  conv_tc_kernel<kCols><<<grid, kConvThreads, smem, st>>>(p);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+static int conv_launch(const ConvParams& p, size_t smem, int tmem_cols, cudaStream_t st) {
+  switch (tmem_cols) {
+    case 32: return conv_launch_t<32>(p, smem, st);
+    case 64: return conv_launch_t<64>(p, smem, st);
+    default: return conv_launch_t<128>(p, smem, st);
+  }
+}
+
+extern "C" int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream) {
+  ConvParams p; size_t smem; int cols;
+  if (conv_fill(d, &p, &smem, &cols)) return 1;
+  return conv_launch(p, smem, cols, (cudaStream_t)stream);
+}
+
+extern "C" int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
+                                    int c0_real, int c0_store, void* stream) {
+  DMD_CHECK(w && wpk, "pack: null pointer");
+  const int total = taps * Cin * CoutPad;
+  pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int dmd_gn_stats(const float* x, double* stats, int B, int HW, int C, int gs, void* stream) {
+  DMD_CHECK(x && stats && gs > 0 && C % gs == 0, "gn_stats: bad arguments");
+  long long per = (long long)HW * C;
+  int chunks = (int)((per + 256 * 64 - 1) / (256 * 64));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  gn_stats_kernel<<<dim3(chunks, B), 256, 0, (cudaStream_t)stream>>>(x, stats, HW, C, gs);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
+  DMD_CHECK(p.C % 8 == 0 && p.C <= 64 && p.L <= 64 && p.L % 32 == 0 && (p.L * p.C) % 256 == 0 && p.C % p.gs == 0,
+            "attn: unsupported shape L=%d C=%d gs=%d (need L in {32,64}, C<=64)", p.L, p.C, p.gs);
+  const size_t smem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * p.C + 1));
+  if (init_kernels()) return 1;
+  attn_kernel<<<B, 256, smem, st>>>(p);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int dmd_attn_fwd(const float* x, const double* stats_in, const float* gamma, const float* beta,
+                            const float* wqkv, const float* bqkv, const float* wout, const float* bout, float* out,
+                            double* out_stats, int B, int L, int C, int gs, float eps, void* stream) {
+  AttnParams p{x, stats_in, gamma, beta, wqkv, bqkv, wout, bout, out, out_stats, L, C, gs, eps};
+  return attn_launch(p, B, (cudaStream_t)stream);
+}
+
+extern "C" int dmd_nchw_to_nhwc(const float* in, float* out, int B, int C, int CP, int HW, void* stream) {
+  nchw_to_nhwc_kernel<<<dim3((HW + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(in, out, C, CP, HW);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+extern "C" int dmd_nhwc_to_nchw(const float* in, float* out, int B, int C, int CP, int HW, void* stream) {
+  nhwc_to_nchw_kernel<<<dim3((HW + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(in, out, C, CP, HW);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- denoiser executor
+namespace {
+
+constexpr float kGnEps = 1e-5f;  // blocks.py:13
+
+struct ConvW {          // one nn.Conv2d
+  int w_idx, b_idx;     // indices into the state_dict pointer list
+  int Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store;
+  size_t pk_off;        // byte offset into the packed-weight buffer
+};
+struct FilmW { int w_idx, b_idx, C, off; };  // AdaGroupNorm.linear ; off = row offset into the batched FiLM GEMM
+struct ResBlockW {
+  int cin, cout;
+  int has_proj; ConvW proj;
+  FilmW n1, n2; ConvW c1, c2;
+  int has_attn; int an_w, an_b, qkv_w, qkv_b, op_w, op_b;
+};
+
+struct Tens { float* data; double* stats; int C, H, W, gs; };
+
+enum OpKind { OP_CONV = 0, OP_ATTN = 1 };
+struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; };
+
+struct Plan {
+  int B = 0, H = 0, W = 0;
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  float *xin = nullptr, *cs = nullptr, *cond = nullptr, *film = nullptr, *fout = nullptr;
+  double* stats = nullptr; size_t stats_bytes = 0;
+  int CP_in = 0, CF = 0;
+  std::vector<Op> ops;
+  // sampler state (NCHW fp32)
+  float *s_obs = nullptr, *s_x[2] = {nullptr, nullptr}, *s_x2 = nullptr, *s_d = nullptr, *s_traj = nullptr, *s_eps = nullptr;
+  int64_t* s_act = nullptr;
+};
+
+struct SamplerGraph {
+  bool valid = false;
+  int B = 0, H = 0, W = 0; void* ws = nullptr; int order = 0; bool has_eps = false;
+  std::vector<float> sigmas; float churn[4] = {0, 0, 0, 0};
+  long long kernels = 0;  // kernel nodes per replay
+  cudaGraphExec_t exec = nullptr;
+};
+
+}  // namespace
+
+struct dmd_denoiser {
+  dmd_denoiser_config cfg;
+  int n_tensors = 0;
+  // state_dict indices
+  int i_fourier = 0, i_actemb = 0, i_cp0w = 0, i_cp0b = 0, i_cp2w = 0, i_cp2b = 0, i_normout_w = 0, i_normout_b = 0;
+  ConvW conv_in, conv_out;
+  std::vector<std::vector<ResBlockW>> d_blocks, u_blocks;
+  std::vector<ResBlockW> mid;
+  std::vector<ConvW> downs, ups;  // index 0 unused (Identity)
+  int film_rows = 0;
+  size_t packed_bytes = 0, film_w_off = 0, film_b_off = 0;
+  std::vector<const float*> ptrs;
+  uint8_t* packed = nullptr;
+  Plan plan;
+  SamplerGraph graph;
+  int need_B = 0, need_H = 0, need_W = 0; size_t need_bytes = 0;
+};
+
+namespace {
+
+struct Walker {  // assigns state_dict indices in module registration order and packed-buffer offsets
+  dmd_denoiser* h; int idx = 0; size_t pk = 0;
+  ConvW conv(int cout, int cin_real, int taps, int c0_real, int c0_store, int c1) {
+    ConvW c; c.w_idx = idx++; c.b_idx = idx++;
+    c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
+    c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16);
+    c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2; pk = (pk + 255) & ~(size_t)255;
+    return c;
+  }
+  FilmW film(int C) { FilmW f; f.w_idx = idx++; f.b_idx = idx++; f.C = C; f.off = h->film_rows; h->film_rows += 2 * C; return f; }
+  // c0/c1: channels of the two concatenated inputs (c1 = 0: single input)
+  ResBlockW resblock(int c0, int c1, int cout, bool attn) {
+    ResBlockW r; r.cin = c0 + c1; r.cout = cout;
+    r.has_proj = (r.cin != cout);
+    if (r.has_proj) r.proj = conv(cout, r.cin, 1, c0, c0, c1);
+    r.n1 = film(r.cin);
+    r.c1 = conv(cout, r.cin, 9, c0, c0, c1);
+    r.n2 = film(cout);
+    r.c2 = conv(cout, cout, 9, cout, cout, 0);
+    r.has_attn = attn;
+    if (attn) { r.an_w = idx++; r.an_b = idx++; r.qkv_w = idx++; r.qkv_b = idx++; r.op_w = idx++; r.op_b = idx++; }
+    return r;
+  }
+};
+
+int build_structure(dmd_denoiser* h) {
+  const dmd_denoiser_config& c = h->cfg;
+  const int L = c.num_levels;
+  Walker w{h};
+  // InnerModel.__init__ registration order (inner_model.py:24-42): noise_emb, act_emb, cond_proj, conv_in, unet,
+  // norm_out, conv_out.  UNet (blocks.py:183-220): d_blocks, u_blocks, mid_blocks, downsamples, upsamples.
+  h->i_fourier = w.idx++; h->i_actemb = w.idx++;
+  h->i_cp0w = w.idx++; h->i_cp0b = w.idx++; h->i_cp2w = w.idx++; h->i_cp2b = w.idx++;
+  const int cin_real = (c.num_steps_conditioning + 1) * c.img_channels;
+  const int cin_store = round_up(cin_real, 8);
+  h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0);
+  h->d_blocks.resize(L);
+  for (int i = 0; i < L; ++i) {
+    const int c1 = c.channels[i > 0 ? i - 1 : 0], c2 = c.channels[i];
+    for (int k = 0; k < c.depths[i]; ++k) h->d_blocks[i].push_back(w.resblock(k == 0 ? c1 : c2, 0, c2, c.attn_depths[i] != 0));
+  }
+  // u_blocks were built per level i then reversed (blocks.py:199-207,209): module order = level L-1 ... 0
+  h->u_blocks.resize(L);
+  for (int m = 0; m < L; ++m) {
+    const int i = L - 1 - m;
+    const int c1 = c.channels[i > 0 ? i - 1 : 0], c2 = c.channels[i];
+    const int n = c.depths[i];
+    // list_in_channels = [2*c2]*n + [c1+c2] ; list_out = [c2]*n + [c1]; the concat is (x, skip) with x first.
+    // x has c2 channels for every block (block n's x is the previous block's output, c2); skips carry c2 except the
+    // last one (the level's x_down, c1 channels).
+    for (int k = 0; k <= n; ++k) h->u_blocks[m].push_back(w.resblock(c2, k < n ? c2 : c1, k < n ? c2 : c1, c.attn_depths[i] != 0));
+  }
+  for (int k = 0; k < 2; ++k) h->mid.push_back(w.resblock(c.channels[L - 1], 0, c.channels[L - 1], true));
+  h->downs.resize(L); h->ups.resize(L);
+  for (int i = 1; i < L; ++i) h->downs[i] = w.conv(c.channels[i - 1], c.channels[i - 1], 9, c.channels[i - 1], c.channels[i - 1], 0);
+  for (int m = 1; m < L; ++m) { const int ch = c.channels[L - 1 - m]; h->ups[m] = w.conv(ch, ch, 9, ch, ch, 0); }
+  h->i_normout_w = w.idx++; h->i_normout_b = w.idx++;
+  h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0);
+  h->n_tensors = w.idx;
+  size_t pk = w.pk;
+  h->film_w_off = pk; pk += (size_t)h->film_rows * c.cond_channels * 4; pk = (pk + 255) & ~(size_t)255;
+  h->film_b_off = pk; pk += (size_t)h->film_rows * 4; pk = (pk + 255) & ~(size_t)255;
+  h->packed_bytes = pk;
+  return 0;
+}
+
+struct Bump {
+  uint8_t* base; size_t off = 0;
+  void* take(size_t bytes) { off = (off + 255) & ~(size_t)255; void* p = base ? base + off : nullptr; off += bytes; return p; }
+};
+
+// -- plan construction: mirrors InnerModel.forward / UNet.forward / ResBlock.forward
+struct PlanBuilder {
+  dmd_denoiser* h; Plan* pl; Bump* bump; Bump* sbump; int err = 0;
+
+  Tens tensor(int C, int H, int W, bool with_stats) {
+    Tens t; t.C = C; t.H = H; t.W = W; t.gs = gn_group_size(C);
+    t.data = (float*)bump->take((size_t)pl->B * H * W * C * 4);
+    t.stats = with_stats ? (double*)sbump->take((size_t)pl->B * (C / t.gs) * 2 * 8) : nullptr;
+    return t;
+  }
+  const float* P(int idx) const { return h->ptrs.empty() ? nullptr : h->ptrs[idx]; }
+
+  void conv(const ConvW& cw, const Tens& a, const Tens* b, int upsample, int stride, int pro, const FilmW* film,
+            int gamma_idx, int beta_idx, bool silu, const Tens* resid, Tens& out, bool out_stats) {
+    dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = a.data; d.C0 = a.C; d.src1 = b ? b->data : nullptr; d.C1 = b ? b->C : 0; d.Cin = cw.Cin;
+    d.B = pl->B; d.Hs = a.H; d.Ws = a.W; d.upsample = upsample; d.taps = cw.taps; d.stride = stride;
+    d.prologue = pro; d.silu = silu;
+    d.stats0 = a.stats; d.gs0 = a.gs; d.stats1 = b ? b->stats : nullptr; d.gs1 = b ? b->gs : 0;
+    if (film) { d.film = pl->film; d.film_stride = h->film_rows; d.film_off = film->off; }
+    if (pro == 2) { d.gamma = P(gamma_idx); d.beta = P(beta_idx); }
+    d.eps = kGnEps;
+    d.wpk = h->packed ? h->packed + cw.pk_off : (const void*)1; d.bias = P(cw.b_idx);
+    d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
+    d.residual = resid ? resid->data : nullptr; d.out = out.data ? out.data : (float*)1;
+    d.out_stats = out_stats ? out.stats : nullptr; d.out_gs = out.gs;
+    if (!d.src0) d.src0 = (const float*)1;
+    if (b && !d.src1) d.src1 = (const float*)1;
+    if (pro && !d.stats0) d.stats0 = (const double*)1;
+    if (pro && b && !d.stats1) d.stats1 = (const double*)1;
+    if (pro == 1 && !d.film) d.film = (const float*)1;
+    if (pro == 2 && !d.gamma) { d.gamma = (const float*)1; d.beta = (const float*)1; }
+    Op op; op.kind = OP_CONV;
+    if (conv_fill(&d, &op.conv, &op.smem, &op.cols)) { err = 1; return; }
+    pl->ops.push_back(op);
+  }
+
+  Tens resblock(const ResBlockW& rb, const Tens& x, const Tens* skip) {
+    const int H = x.H, W = x.W;
+    Tens r;
+    if (rb.has_proj) { r = tensor(rb.cout, H, W, false); conv(rb.proj, x, skip, 0, 1, 0, nullptr, 0, 0, false, nullptr, r, false); }
+    else r = x;
+    Tens t = tensor(rb.cout, H, W, true);
+    conv(rb.c1, x, skip, 0, 1, 1, &rb.n1, 0, 0, true, nullptr, t, true);
+    Tens o = tensor(rb.cout, H, W, true);
+    conv(rb.c2, t, nullptr, 0, 1, 1, &rb.n2, 0, 0, true, &r, o, true);
+    if (!rb.has_attn) return o;
+    Tens a = tensor(rb.cout, H, W, true);
+    Op op; op.kind = OP_ATTN;
+    op.attn = AttnParams{o.data, o.stats, P(rb.an_w), P(rb.an_b), P(rb.qkv_w), P(rb.qkv_b), P(rb.op_w), P(rb.op_b), a.data, a.stats, H * W, rb.cout, o.gs, kGnEps};
+    pl->ops.push_back(op);
+    return a;
+  }
+
+  int build() {
+    const dmd_denoiser_config& c = h->cfg;
+    const int L = c.num_levels, B = pl->B, H = pl->H, W = pl->W;
+    const int div = 1 << (L - 1);
+    if (H % div || W % div) return fail("denoiser: H=%d W=%d must be multiples of %d (UNet pad path, blocks.py:225-229, not built yet)", H, W, div);
+    pl->CP_in = h->conv_in.c0_store;
+    pl->xin = (float*)bump->take((size_t)B * H * W * pl->CP_in * 4);
+    pl->cs = (float*)bump->take((size_t)(B + 1) * 4 * 4);  // +1: scalar sigma slot used by the sampler
+    pl->cond = (float*)bump->take((size_t)B * c.cond_channels * 4);
+    pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
+    Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
+    Tens x = tensor(c.channels[0], H, W, true);
+    conv(h->conv_in, xin, nullptr, 0, 1, 0, nullptr, 0, 0, false, nullptr, x, true);
+    std::vector<std::vector<Tens>> d_outputs;
+    for (int i = 0; i < L; ++i) {
+      Tens xd = x;
+      if (i > 0) { xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true); conv(h->downs[i], x, nullptr, 0, 2, 0, nullptr, 0, 0, false, nullptr, xd, true); }
+      std::vector<Tens> outs{xd};
+      x = xd;
+      for (auto& rb : h->d_blocks[i]) { x = resblock(rb, x, nullptr); outs.push_back(x); }
+      d_outputs.push_back(outs);
+    }
+    for (auto& rb : h->mid) x = resblock(rb, x, nullptr);
+    for (int m = 0; m < L; ++m) {
+      Tens xu = x;
+      if (m > 0) { xu = tensor(x.C, x.H * 2, x.W * 2, true); conv(h->ups[m], x, nullptr, 1, 1, 0, nullptr, 0, 0, false, nullptr, xu, true); }
+      x = xu;
+      const std::vector<Tens>& skip = d_outputs[L - 1 - m];  // reversed(d_outputs); block k uses skip[::-1][k]
+      const int ns = (int)skip.size();
+      for (size_t k = 0; k < h->u_blocks[m].size(); ++k) x = resblock(h->u_blocks[m][k], x, &skip[ns - 1 - (int)k]);
+    }
+    pl->CF = c.img_channels;
+    pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
+    Tens f{pl->fout, nullptr, pl->CF, H, W, pl->CF};
+    conv(h->conv_out, x, nullptr, 0, 1, 2, nullptr, h->i_normout_w, h->i_normout_b, true, nullptr, f, false);
+    // sampler buffers
+    const size_t img = (size_t)B * c.img_channels * H * W * 4;
+    pl->s_obs = (float*)bump->take(img * c.num_steps_conditioning);
+    pl->s_act = (int64_t*)bump->take((size_t)B * c.num_steps_conditioning * 8);
+    pl->s_x[0] = (float*)bump->take(img); pl->s_x[1] = (float*)bump->take(img);
+    pl->s_x2 = (float*)bump->take(img); pl->s_d = (float*)bump->take(img);
+    return err;
+  }
+};
+
+int make_plan(dmd_denoiser* h, Plan* pl, int B, int H, int W, uint8_t* base, size_t* total) {
+  pl->B = B; pl->H = H; pl->W = W; pl->ops.clear();
+  // pass 1: stats region size (tiny) — run the builder on null bases
+  Bump b0{nullptr}, s0{nullptr};
+  { Plan tmp; tmp.B = B; tmp.H = H; tmp.W = W; PlanBuilder pb{h, &tmp, &b0, &s0}; if (pb.build()) return 1; }
+  const size_t stats_bytes = (s0.off + 255) & ~(size_t)255;
+  if (total) *total = stats_bytes + b0.off + 256;
+  if (!base) return 0;
+  Bump sb{base}, bb{base + stats_bytes};
+  pl->base = base; pl->stats = (double*)base; pl->stats_bytes = stats_bytes;
+  PlanBuilder pb{h, pl, &bb, &sb};
+  if (pb.build()) return 1;
+  pl->bytes = stats_bytes + bb.off;
+  return 0;
+}
+
+int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigma, int sigma_is_scalar, const float* obs,
+                const int64_t* act, cudaStream_t st, int prescaled = 0) {
+  const dmd_denoiser_config& c = h->cfg;
+  const int HW = pl.H * pl.W;
+  DMD_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st));
+  pack_denoiser_input_kernel<<<dim3((HW + 255) / 256, pl.B), 256, 0, st>>>(
+      noisy, obs, sigma, sigma_is_scalar, pl.xin, pl.cs, c.num_steps_conditioning * c.img_channels, c.img_channels,
+      pl.CP_in, HW, c.sigma_data, c.sigma_offset_noise, prescaled);
+  DMD_LAUNCH_OK();
+  cond_kernel<<<pl.B, 256, 2 * c.cond_channels * sizeof(float), st>>>(
+      pl.cs, act, h->ptrs[h->i_fourier], h->ptrs[h->i_actemb], h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b],
+      h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, c.cond_channels, c.num_steps_conditioning, c.num_actions);
+  DMD_LAUNCH_OK();
+  film_kernel<<<dim3((h->film_rows + 63) / 64, (pl.B + 31) / 32), 256, (size_t)c.cond_channels * 32 * sizeof(float), st>>>(
+      pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film, pl.B,
+      c.cond_channels, h->film_rows);
+  DMD_LAUNCH_OK();
+  for (const Op& op : pl.ops) {
+    if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
+    else { if (attn_launch(op.attn, pl.B, st)) return 1; }
+  }
+  return 0;
+}
+
+int run_wrap(dmd_denoiser* h, Plan& pl, const float* x, float* model_out, float* denoised, float* x_out, float* d_out,
+             const float* d_prev, const float* x0, int mode, float sigma_hat, float dt, cudaStream_t st) {
+  const int HW = pl.H * pl.W, total = pl.B * h->cfg.img_channels * HW;
+  wrap_update_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.fout, x, pl.cs, model_out, denoised, x_out, d_out, d_prev, x0,
+                                                         mode, sigma_hat, dt, h->cfg.img_channels, pl.CF, HW, total);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+int ensure_plan(dmd_denoiser* h, int B, int H, int W, void* ws, size_t ws_bytes) {
+  DMD_CHECK(!h->ptrs.empty() && h->packed, "denoiser: call dmd_denoiser_set_weights first");
+  Plan& pl = h->plan;
+  if (pl.B == B && pl.H == H && pl.W == W && pl.base == (uint8_t*)ws) return 0;
+  size_t need = 0;
+  if (make_plan(h, &pl, B, H, W, nullptr, &need)) return 1;
+  DMD_CHECK(ws && ws_bytes >= need, "denoiser: workspace too small (%zu < %zu)", ws_bytes, need);
+  DMD_CHECK(((uintptr_t)ws & 255) == 0, "denoiser: workspace must be 256-byte aligned");
+  if (make_plan(h, &pl, B, H, W, (uint8_t*)ws, nullptr)) { pl.B = 0; return 1; }
+  h->graph.valid = false;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" dmd_denoiser* dmd_denoiser_create(const dmd_denoiser_config* cfg) {
+  if (!cfg || cfg->num_levels < 1 || cfg->num_levels > DMD_MAX_LEVELS) { fail("denoiser_create: bad config"); return nullptr; }
+  if (cfg->cond_channels % 32 || cfg->cond_channels > 1024 || cfg->cond_channels % cfg->num_steps_conditioning) { fail("denoiser_create: cond_channels must be a multiple of 32 and of num_steps_conditioning"); return nullptr; }
+  for (int i = 0; i < cfg->num_levels; ++i)
+    if (cfg->channels[i] % 32 || cfg->channels[i] > 64) { fail("denoiser_create: channels must be 32 or 64 per level (got %d)", cfg->channels[i]); return nullptr; }
+  if (init_kernels()) return nullptr;
+  dmd_denoiser* h = new dmd_denoiser();
+  h->cfg = *cfg;
+  build_structure(h);
+  return h;
+}
+extern "C" void dmd_denoiser_destroy(dmd_denoiser* h) {
+  if (!h) return;
+  if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+  delete h;
+}
+extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_tensors; }
+extern "C" size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h) { return h->packed_bytes; }
+
+static int pack_one(dmd_denoiser* h, const ConvW& c, cudaStream_t st) {
+  return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, st);
+}
+static int pack_rb(dmd_denoiser* h, const ResBlockW& r, cudaStream_t st) {
+  const int CC = h->cfg.cond_channels;
+  if (r.has_proj && pack_one(h, r.proj, st)) return 1;
+  if (pack_one(h, r.c1, st) || pack_one(h, r.c2, st)) return 1;
+  for (const FilmW* f : {&r.n1, &r.n2}) {
+    DMD_CUDA(cudaMemcpyAsync(h->packed + h->film_w_off + (size_t)f->off * CC * 4, h->ptrs[f->w_idx], (size_t)2 * f->C * CC * 4, cudaMemcpyDeviceToDevice, st));
+    DMD_CUDA(cudaMemcpyAsync(h->packed + h->film_b_off + (size_t)f->off * 4, h->ptrs[f->b_idx], (size_t)2 * f->C * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+extern "C" int dmd_denoiser_set_weights(dmd_denoiser* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream) {
+  DMD_CHECK(h && ptrs_host && packed, "set_weights: null argument");
+  DMD_CHECK(n_ptrs == h->n_tensors, "set_weights: expected %d tensors (InnerModel.state_dict order), got %d", h->n_tensors, n_ptrs);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool moved = h->packed != (uint8_t*)packed || h->ptrs.empty() || memcmp(h->ptrs.data(), ptrs_host, sizeof(float*) * n_ptrs) != 0;
+  h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
+  h->packed = (uint8_t*)packed;
+  if (moved) { h->plan.B = 0; h->graph.valid = false; }
+  if (pack_one(h, h->conv_in, st) || pack_one(h, h->conv_out, st)) return 1;
+  for (auto& lv : h->d_blocks) for (auto& r : lv) if (pack_rb(h, r, st)) return 1;
+  for (auto& lv : h->u_blocks) for (auto& r : lv) if (pack_rb(h, r, st)) return 1;
+  for (auto& r : h->mid) if (pack_rb(h, r, st)) return 1;
+  for (int i = 1; i < h->cfg.num_levels; ++i) if (pack_one(h, h->downs[i], st) || pack_one(h, h->ups[i], st)) return 1;
+  return 0;
+}
+
+extern "C" size_t dmd_denoiser_workspace_bytes(const dmd_denoiser* h, int B, int H, int W) {
+  Plan tmp; size_t need = 0;
+  if (make_plan(const_cast<dmd_denoiser*>(h), &tmp, B, H, W, nullptr, &need)) return 0;
+  return need;
+}
+
+extern "C" int dmd_denoiser_forward(dmd_denoiser* h, int B, int H, int W, const float* noisy, const float* sigma,
+                                    int sigma_is_scalar, const float* obs, const int64_t* act, float* out_model,
+                                    float* out_denoised, void* workspace, size_t workspace_bytes, void* stream) {
+  DMD_CHECK(h && noisy && sigma && obs && act, "denoiser_forward: null argument");
+  if (ensure_plan(h, B, H, W, workspace, workspace_bytes)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (run_forward(h, h->plan, noisy, sigma, sigma_is_scalar, obs, act, st)) return 1;
+  return run_wrap(h, h->plan, noisy, out_model, out_denoised, nullptr, nullptr, nullptr, nullptr, 0, 1.f, 0.f, st);
+}
+
+extern "C" int dmd_inner_model_forward(dmd_denoiser* h, int B, int H, int W, const float* noisy_rescaled,
+                                       const float* c_noise, int c_noise_is_scalar, const float* obs_rescaled,
+                                       const int64_t* act, float* out, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  DMD_CHECK(h && noisy_rescaled && c_noise && obs_rescaled && act && out, "inner_model_forward: null argument");
+  if (ensure_plan(h, B, H, W, workspace, workspace_bytes)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (run_forward(h, h->plan, noisy_rescaled, c_noise, c_noise_is_scalar, obs_rescaled, act, st, 1)) return 1;
+  return run_wrap(h, h->plan, noisy_rescaled, out, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1.f, 0.f, st);
+}
+
+// ---------------------------------------------------------------------------------------------- sampler
+namespace {
+
+__global__ void fill_scalar_kernel(float* p, float v) { *p = v; }
+
+int sampler_body(dmd_denoiser* h, const dmd_sampler_config* sc, bool has_eps, cudaStream_t st) {
+  Plan& pl = h->plan;
+  const int n = sc->num_sigmas;
+  const size_t img_elems = (size_t)pl.B * h->cfg.img_channels * pl.H * pl.W;
+  const int total = (int)img_elems;
+  // diffusion_sampler.py:35  gamma_ = min(s_churn / (len(sigmas) - 1), 2**0.5 - 1)
+  const double gamma_ = std::fmin((double)sc->s_churn / (double)(n - 1), std::sqrt(2.0) - 1.0);
+  float* sig_dev = pl.cs + (size_t)pl.B * 4;  // one spare float4 slot after cs (see make_plan: +256 B slack)
+  int cur = 0;
+  for (int i = 0; i + 1 < n; ++i) {
+    const float sigma = sc->sigmas_host[i], next_sigma = sc->sigmas_host[i + 1];
+    const double gamma = (sc->s_tmin <= sigma && sigma <= sc->s_tmax) ? gamma_ : 0.0;
+    const float sigma_hat = sigma * (float)(gamma + 1.0);
+    float* x = pl.s_x[cur];
+    if (gamma > 0.0) {
+      DMD_CHECK(has_eps, "sampler: s_churn > 0 needs eps noise from the caller");
+      const float cfac = std::sqrt(sigma_hat * sigma_hat - sigma * sigma);
+      // x = x + (eps * s_noise) * c   (two roundings as in the reference); s_noise folded when it is exactly 1
+      DMD_CHECK(sc->s_noise == 1.0f, "sampler: s_noise != 1 not built yet");
+      axpy_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, pl.s_eps + (size_t)i * img_elems, cfac, x, total);
+      DMD_LAUNCH_OK();
+    }
+    fill_scalar_kernel<<<1, 1, 0, st>>>(sig_dev, sigma);
+    DMD_LAUNCH_OK();
+    if (run_forward(h, pl, x, sig_dev, 1, pl.s_obs, pl.s_act, st)) return 1;
+    const float dt = next_sigma - sigma_hat;
+    float* xn = pl.s_x[cur ^ 1];
+    if (sc->order == 1 || next_sigma == 0.0f) {
+      if (run_wrap(h, pl, x, nullptr, nullptr, xn, nullptr, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
+    } else {
+      // Heun: x_2 = x + d*dt ; denoise(x_2, next_sigma) ; x = x + ((d + d_2)/2)*dt
+      if (run_wrap(h, pl, x, nullptr, nullptr, pl.s_x2, pl.s_d, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
+      fill_scalar_kernel<<<1, 1, 0, st>>>(sig_dev, next_sigma);
+      DMD_LAUNCH_OK();
+      if (run_forward(h, pl, pl.s_x2, sig_dev, 1, pl.s_obs, pl.s_act, st)) return 1;
+      if (run_wrap(h, pl, pl.s_x2, nullptr, nullptr, xn, nullptr, pl.s_d, x, 2, next_sigma, dt, st)) return 1;
+    }
+    cur ^= 1;
+    if (pl.s_traj) DMD_CUDA(cudaMemcpyAsync(pl.s_traj + (size_t)(i + 1) * img_elems, pl.s_x[cur], img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (cur != 0) DMD_CUDA(cudaMemcpyAsync(pl.s_x[0], pl.s_x[1], img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int H, int W,
+                                  const float* prev_obs, const int64_t* prev_act, const float* x0, const float* eps,
+                                  float* out_x, float* out_traj, void* workspace, size_t workspace_bytes, int use_graph,
+                                  void* stream) {
+  DMD_CHECK(h && sc && prev_obs && prev_act && x0 && out_x, "sampler: null argument");
+  DMD_CHECK(sc->num_sigmas >= 2 && sc->sigmas_host, "sampler: need at least 2 sigmas");
+  DMD_CHECK(sc->order == 1 || sc->order == 2, "sampler: order must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dmd_denoiser_config& c = h->cfg;
+  const size_t img_elems = (size_t)B * c.img_channels * H * W;
+  const int n = sc->num_sigmas;
+  if (init_kernels()) return 1;
+  // the trajectory / eps staging buffers live at the tail of the workspace
+  if (h->need_B != B || h->need_H != H || h->need_W != W) {
+    h->need_bytes = dmd_denoiser_workspace_bytes(h, B, H, W);
+    h->need_B = B; h->need_H = H; h->need_W = W;
+  }
+  const size_t core = h->need_bytes;
+  DMD_CHECK(core > 0, "sampler: %s", g_err.c_str());
+  const size_t traj_bytes = img_elems * 4 * n, eps_bytes = eps ? img_elems * 4 * (n - 1) : 0;
+  DMD_CHECK(workspace_bytes >= core + traj_bytes + eps_bytes + 512, "sampler: workspace too small (%zu < %zu)", workspace_bytes, core + traj_bytes + eps_bytes + 512);
+  if (ensure_plan(h, B, H, W, workspace, core)) return 1;
+  Plan& pl = h->plan;
+  uint8_t* tail = (uint8_t*)workspace + ((core + 255) & ~(size_t)255);
+  pl.s_traj = (float*)tail;
+  pl.s_eps = eps ? (float*)(tail + ((traj_bytes + 255) & ~(size_t)255)) : nullptr;
+
+  DMD_CUDA(cudaMemcpyAsync(pl.s_obs, prev_obs, img_elems * 4 * c.num_steps_conditioning, cudaMemcpyDeviceToDevice, st));
+  DMD_CUDA(cudaMemcpyAsync(pl.s_act, prev_act, (size_t)B * c.num_steps_conditioning * 8, cudaMemcpyDeviceToDevice, st));
+  DMD_CUDA(cudaMemcpyAsync(pl.s_x[0], x0, img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  DMD_CUDA(cudaMemcpyAsync(pl.s_traj, x0, img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  if (eps) DMD_CUDA(cudaMemcpyAsync(pl.s_eps, eps, eps_bytes, cudaMemcpyDeviceToDevice, st));
+
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  DMD_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (!use_graph || cap != cudaStreamCaptureStatusNone) {
+    if (sampler_body(h, sc, eps != nullptr, st)) return 1;
+  } else {
+    SamplerGraph& g = h->graph;
+    const float churn[4] = {sc->s_churn, sc->s_tmin, sc->s_tmax, sc->s_noise};
+    bool same = g.valid && g.B == B && g.H == H && g.W == W && g.ws == workspace && g.order == sc->order &&
+                g.has_eps == (eps != nullptr) && (int)g.sigmas.size() == n &&
+                memcmp(g.sigmas.data(), sc->sigmas_host, 4 * n) == 0 && memcmp(g.churn, churn, sizeof(churn)) == 0;
+    if (!same) {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      g.valid = false;
+      cudaGraph_t graph = nullptr;
+      DMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const long long before = g_launches;
+      int rc = sampler_body(h, sc, eps != nullptr, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      g.kernels = g_launches - before;
+      g_launches = before;  // capture does not execute
+      if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+      DMD_CHECK(ce == cudaSuccess, "sampler: graph capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      DMD_CHECK(ce == cudaSuccess, "sampler: graph instantiate failed: %s", cudaGetErrorString(ce));
+      g.valid = true; g.B = B; g.H = H; g.W = W; g.ws = workspace; g.order = sc->order; g.has_eps = eps != nullptr;
+      g.sigmas.assign(sc->sigmas_host, sc->sigmas_host + n); memcpy(g.churn, churn, sizeof(churn));
+    }
+    DMD_CUDA(cudaGraphLaunch(g.exec, st));
+    g_launches += g.kernels;
+  }
+  DMD_CUDA(cudaMemcpyAsync(out_x, pl.s_x[0], img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_traj) DMD_CUDA(cudaMemcpyAsync(out_traj, pl.s_traj, traj_bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

@@ -1,0 +1,145 @@
+/* diamond_b200 — C ABI of the B200-native DIAMOND hot path (libdiamond_b200.so).
+ *
+ * The reference (eloialonso/diamond @ 5bcd159) is pure Python and has no FFI of its own; the
+ * seam is its Python module surface.  Every entry point below therefore names the reference call site it replaces.
+ * The Python mirror in diamond_b200/ binds these with ctypes (see INTEGRATION.md for the stub a maintainer adds).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; activations are fp32
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, never synchronise the device and never
+ *     allocate on the hot path (the caller owns every buffer, including the workspace)
+ *   - return value 0 = ok; nonzero = error, message via dmd_last_error() (thread-local)
+ *   - one host thread per GPU (the reference is one process per rank, src/main.py:26)
+ */
+#ifndef DIAMOND_B200_H_
+#define DIAMOND_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMD_VERSION 100
+
+int dmd_version(void);
+const char* dmd_last_error(void);
+/* Number of kernels launched by this library on the calling thread since the last reset (bench.py gpu_launches). */
+long long dmd_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Per-op entry points (NHWC fp32 activations).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces nn.Conv2d weight use (src/models/blocks.py:18-19,96): packs a torch-layout weight [Cout][CinReal][k][k]
+ * into the fp16 tensor-core operand layout [taps][Cin/8][CoutPad][8].  c0_real/c0_store describe a zero-padded first
+ * source (e.g. 15 real channels stored as 16); for a single unpadded source pass c0_real = c0_store = CinReal. */
+int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
+                         int c0_real, int c0_store, void* stream);
+
+typedef struct dmd_conv_desc {
+  const float* src0;     /* NHWC [B][Hs][Ws][C0] */
+  const float* src1;     /* NHWC [B][Hs][Ws][C1] or NULL  (channel concat, blocks.py:174) */
+  int C0, C1, Cin;       /* Cin = K extent per tap, multiple of 16, >= C0 + C1 */
+  int B, Hs, Ws;
+  int upsample;          /* 1: nearest x2 before the conv (blocks.py:109) */
+  int taps;              /* 9 = 3x3 pad 1 ; 1 = 1x1 */
+  int stride;            /* 1 or 2 (blocks.py:96) */
+  int prologue;          /* 0 none ; 1 AdaGroupNorm (blocks.py:43-45) ; 2 affine GroupNorm (blocks.py:28) */
+  int silu;              /* SiLU after the prologue (blocks.py:119,143-144; inner_model.py:48) */
+  const double* stats0;  /* [B][C0/gs0][2] (sum, sumsq) of src0 over (Hs*Ws*gs0) */
+  const double* stats1;
+  int gs0, gs1;
+  const float* film;     /* [B][film_stride] ; scale at film_off + c, shift at film_off + (C0+C1) + c */
+  int film_stride, film_off;
+  const float* gamma;    /* affine GroupNorm weight / bias [C0+C1] */
+  const float* beta;
+  float eps;
+  const void* wpk;       /* from dmd_pack_conv_weight */
+  const float* bias;     /* [Cout] or NULL */
+  int Cout, CoutPad;     /* CoutPad: multiple of 16, <= 128 */
+  const float* residual; /* NHWC like out, or NULL (blocks.py:145) */
+  float* out;            /* NHWC [B][Ho][Wo][Cout] */
+  double* out_stats;     /* [B][Cout/out_gs][2], accumulated (caller zeroes) or NULL */
+  int out_gs;
+  int debug;             /* bring-up only; 0 */
+} dmd_conv_desc;
+
+int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);
+
+/* GroupNorm partial sums of an NHWC tensor: stats[n][g] += (sum, sumsq) (blocks.py:28,43). */
+int dmd_gn_stats(const float* x, double* stats, int B, int HW, int C, int gs, void* stream);
+
+/* SelfAttention2d.forward (blocks.py:62-72), L = H*W <= 64 tokens, C <= 64, head_dim 8. */
+int dmd_attn_fwd(const float* x, const double* stats_in, const float* gamma, const float* beta, const float* wqkv,
+                 const float* bqkv, const float* wout, const float* bout, float* out, double* out_stats, int B, int L,
+                 int C, int gs, float eps, void* stream);
+
+int dmd_nchw_to_nhwc(const float* in, float* out, int B, int C, int CP, int HW, void* stream);
+int dmd_nhwc_to_nchw(const float* in, float* out, int B, int C, int CP, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Denoiser executor: InnerModel.forward (inner_model.py:44-49) + Denoiser.denoise (denoiser.py:86-91) +
+ * DiffusionSampler.sample (diffusion_sampler.py:31-58) as one plan of kernels, replayed as a CUDA graph.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define DMD_MAX_LEVELS 8
+
+typedef struct dmd_denoiser_config {
+  int img_channels;             /* InnerModelConfig.img_channels */
+  int num_steps_conditioning;   /* frame stack */
+  int cond_channels;
+  int num_levels;
+  int depths[DMD_MAX_LEVELS];
+  int channels[DMD_MAX_LEVELS];
+  int attn_depths[DMD_MAX_LEVELS];
+  int num_actions;
+  float sigma_data;             /* DenoiserConfig */
+  float sigma_offset_noise;
+} dmd_denoiser_config;
+
+typedef struct dmd_denoiser dmd_denoiser;
+
+dmd_denoiser* dmd_denoiser_create(const dmd_denoiser_config* cfg);
+void dmd_denoiser_destroy(dmd_denoiser* h);
+
+/* Number of parameter/buffer tensors expected by dmd_denoiser_set_weights == len(InnerModel.state_dict()). */
+int dmd_denoiser_num_tensors(const dmd_denoiser* h);
+/* Bytes of device memory needed for packed weights (caller allocates, passes to set_weights). */
+size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h);
+/* ptrs_host: host array of device pointers, in InnerModel.state_dict() order (fp32, torch layouts).
+ * Re-packs the tensor-core copies; call again after every optimizer step / load_state_dict. */
+int dmd_denoiser_set_weights(dmd_denoiser* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream);
+
+size_t dmd_denoiser_workspace_bytes(const dmd_denoiser* h, int B, int H, int W);
+
+/* One Denoiser.denoise / compute_model_output call.  noisy (B,C,H,W), sigma (B) or (1), obs (B,T*C,H,W),
+ * act (B,T) int64.  out_model / out_denoised are NCHW (B,C,H,W); either may be NULL. */
+int dmd_denoiser_forward(dmd_denoiser* h, int B, int H, int W, const float* noisy, const float* sigma,
+                         int sigma_is_scalar, const float* obs, const int64_t* act, float* out_model,
+                         float* out_denoised, void* workspace, size_t workspace_bytes, void* stream);
+
+/* InnerModel.forward (inner_model.py:44-49): inputs already rescaled by the caller (denoiser.py:75-76), c_noise (B) or
+ * (1).  out: (B,C,H,W) NCHW model output. */
+int dmd_inner_model_forward(dmd_denoiser* h, int B, int H, int W, const float* noisy_rescaled, const float* c_noise,
+                            int c_noise_is_scalar, const float* obs_rescaled, const int64_t* act, float* out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct dmd_sampler_config {
+  int num_sigmas;               /* len(self.sigmas) = num_steps_denoising + 1, last one 0 */
+  const float* sigmas_host;     /* host array, fp32 values of DiffusionSampler.sigmas */
+  int order;                    /* 1 Euler, 2 Heun */
+  float s_churn, s_tmin, s_tmax, s_noise;
+} dmd_sampler_config;
+
+/* DiffusionSampler.sample.  x0: the initial randn (B,C,H,W) (diffusion_sampler.py:36) and eps: churn noise
+ * (num_steps,B,C,H,W) or NULL are drawn by the CALLER with torch so that RNG streams match the reference.
+ * out_x (B,C,H,W); out_traj (num_sigmas,B,C,H,W) or NULL. */
+int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int H, int W, const float* prev_obs,
+                       const int64_t* prev_act, const float* x0, const float* eps, float* out_x, float* out_traj,
+                       void* workspace, size_t workspace_bytes, int use_graph, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIAMOND_B200_H_ */
