@@ -64,7 +64,10 @@ def test_denoiser_matches_reference_golden(golden_dir, name):
     assert err < REL_TOL, err
     diff = (dn.cpu() - ref_dn).abs()
     assert float(diff.max()) <= 2 / 255 + 1e-6          # never more than one quantisation level
-    assert float((diff > 0).float().mean()) < 0.02      # bucket-edge flips only
+    # P(flip) ~= E|c_out * F_err| / bucket = (1e-3 * 0.5 * ~0.45) / (2/255) ~= 3 % at the 1e-3 tolerance itself
+    flips = float((diff > 0).float().mean())
+    print(f"{name}: denoised pixels one level off = {flips:.3%}")
+    assert flips < 0.05
     # public surface: Denoiser.denoise and InnerModel.forward agree with the fused entry point
     dn2 = den.denoise(x_noisy.to(dev), sig.to(dev), obs.reshape(b, t * ch, h, w).to(dev), act.to(dev))
     assert torch.equal(dn2, dn)
