@@ -34,7 +34,7 @@ static int fail(const char* fmt, ...) {
 #define DMD_CUDA(expr)                                                                   \
   do {                                                                                   \
     cudaError_t e__ = (expr);                                                            \
-    if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    if (e__ != cudaSuccess) { (void)cudaGetLastError(); return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); } \
   } while (0)
 #define DMD_LAUNCH_OK()                                                                 \
   do {                                                                                  \
@@ -226,6 +226,7 @@ struct SamplerGraph {
   std::vector<float> sigmas; float churn[4] = {0, 0, 0, 0};
   long long kernels = 0;  // kernel nodes per replay
   cudaGraphExec_t exec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // capture never happens on the caller's stream (torch's default is the legacy stream)
 };
 
 }  // namespace
@@ -498,6 +499,7 @@ extern "C" dmd_denoiser* dmd_denoiser_create(const dmd_denoiser_config* cfg) {
 extern "C" void dmd_denoiser_destroy(dmd_denoiser* h) {
   if (!h) return;
   if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+  if (h->graph.cap_stream) cudaStreamDestroy(h->graph.cap_stream);
   delete h;
 }
 extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_tensors; }
@@ -658,10 +660,11 @@ extern "C" int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc,
       if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
       g.valid = false;
       cudaGraph_t graph = nullptr;
-      DMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      if (!g.cap_stream) DMD_CUDA(cudaStreamCreateWithFlags(&g.cap_stream, cudaStreamNonBlocking));
+      DMD_CUDA(cudaStreamBeginCapture(g.cap_stream, cudaStreamCaptureModeThreadLocal));
       const long long before = g_launches;
-      int rc = sampler_body(h, sc, eps != nullptr, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      int rc = sampler_body(h, sc, eps != nullptr, g.cap_stream);
+      cudaError_t ce = cudaStreamEndCapture(g.cap_stream, &graph);
       g.kernels = g_launches - before;
       g_launches = before;  // capture does not execute
       if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
