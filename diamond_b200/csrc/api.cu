@@ -94,22 +94,38 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   p->Q = (int)Q;
   const int halo = d->taps == 9 ? p->PW + 1 : 0;
   p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
+  DMD_CHECK(p->P <= 128 * kMaxPosPerThread, "conv: W=%d too wide for the linear halo (P=%d > %d); needs the strip path", p->W, p->P, 128 * kMaxPosPerThread);
   DMD_CHECK((p->P + p->PH * p->PW - 1) / (p->PH * p->PW) + 1 <= kMaxImgSlots, "conv: image too small for tile (H=%d W=%d)", p->H, p->W);
   p->dPW.init(p->PW); p->dPH.init(p->PH);
-  const ConvSmemLayout L = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc);
-  DMD_CHECK(L.total <= 227 * 1024, "conv: needs %u B shared memory (> 227 KB): W=%d Cin=%d", L.total, p->W, p->Cin);
+  p->num_tiles = (p->Q + kTileM - 1) / kTileM;
+  // slab ring depth: as many 16-channel slabs as fit next to the resident weights, at most two tiles' worth
+  const int kslabs = p->Cin / 16;
+  const ConvSmemLayout L0 = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, 0);
+  const long long budget = 227ll * 1024 - (long long)L0.total;
+  int stages = (int)(budget / (long long)L0.slab_bytes);
+  if (stages > 2 * kslabs) stages = 2 * kslabs;
+  if (stages > kMaxStages) stages = kMaxStages;
+  DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
+  p->stages = stages;
+  const ConvSmemLayout L = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, stages);
   *smem = L.total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
   return 0;
 }
 
+static int g_num_sms = 0;
 static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (never during stream capture)
   static bool done = false;
   if (done) return 0;
+  int dev = 0;
+  DMD_CUDA(cudaGetDevice(&dev));
+  DMD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   done = true;
   return 0;
 }
@@ -117,7 +133,7 @@ static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (nev
 template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
-  const int grid = (p.Q + kTileM - 1) / kTileM;
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
   conv_tc_kernel<kCols><<<grid, kConvThreads, smem, st>>>(p);
   DMD_LAUNCH_OK();
   return 0;
@@ -157,11 +173,20 @@ extern "C" int dmd_gn_stats(const float* x, double* stats, int B, int HW, int C,
 }
 
 static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
-  DMD_CHECK(p.C % 8 == 0 && p.C <= 64 && p.L <= 64 && p.L % 32 == 0 && (p.L * p.C) % 256 == 0 && p.C % p.gs == 0,
-            "attn: unsupported shape L=%d C=%d gs=%d (need L in {32,64}, C<=64)", p.L, p.C, p.gs);
-  const size_t smem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * p.C + 1));
+  DMD_CHECK((p.C == 64 || p.C == 32) && p.L == kAttnL && p.C % p.gs == 0 && p.gs % 8 == 0,
+            "attn: unsupported shape L=%d C=%d gs=%d (built for 8x8 = 64 tokens, C in {32, 64})", p.L, p.C, p.gs);
   if (init_kernels()) return 1;
-  attn_kernel<<<B, 256, smem, st>>>(p);
+  const size_t smem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * p.C + 4));
+  if (p.C == 64) attn_kernel<64><<<B, kAttnThreads, smem, st>>>(p);
+  else attn_kernel<32><<<B, kAttnThreads, smem, st>>>(p);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+static int linear_launch(const float* in, const float* W, const float* bias, float* out, int B, int K, int F, int silu, cudaStream_t st) {
+  DMD_CHECK(K % 4 == 0 && K <= 256, "linear: K=%d must be a multiple of 4 and <= 256", K);
+  if (init_kernels()) return 1;
+  linear_kernel<<<dim3((F + 31) / 32, (B + 31) / 32), 256, (size_t)64 * K * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -211,7 +236,7 @@ struct Plan {
   int B = 0, H = 0, W = 0;
   uint8_t* base = nullptr;
   size_t bytes = 0;
-  float *xin = nullptr, *cs = nullptr, *cond = nullptr, *film = nullptr, *fout = nullptr;
+  float *xin = nullptr, *cs = nullptr, *cemb = nullptr, *chid = nullptr, *cond = nullptr, *film = nullptr, *fout = nullptr;
   double* stats = nullptr; size_t stats_bytes = 0;
   int CP_in = 0, CF = 0;
   std::vector<Op> ops;
@@ -384,6 +409,8 @@ struct PlanBuilder {
     pl->CP_in = h->conv_in.c0_store;
     pl->xin = (float*)bump->take((size_t)B * H * W * pl->CP_in * 4);
     pl->cs = (float*)bump->take((size_t)(B + 1) * 4 * 4);  // +1: scalar sigma slot used by the sampler
+    pl->cemb = (float*)bump->take((size_t)B * c.cond_channels * 4);
+    pl->chid = (float*)bump->take((size_t)B * c.cond_channels * 4);
     pl->cond = (float*)bump->take((size_t)B * c.cond_channels * 4);
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
@@ -446,14 +473,16 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
       noisy, obs, sigma, sigma_is_scalar, pl.xin, pl.cs, c.num_steps_conditioning * c.img_channels, c.img_channels,
       pl.CP_in, HW, c.sigma_data, c.sigma_offset_noise, prescaled);
   DMD_LAUNCH_OK();
-  cond_kernel<<<pl.B, 256, 2 * c.cond_channels * sizeof(float), st>>>(
-      pl.cs, act, h->ptrs[h->i_fourier], h->ptrs[h->i_actemb], h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b],
-      h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, c.cond_channels, c.num_steps_conditioning, c.num_actions);
-  DMD_LAUNCH_OK();
-  film_kernel<<<dim3((h->film_rows + 63) / 64, (pl.B + 31) / 32), 256, (size_t)c.cond_channels * 32 * sizeof(float), st>>>(
-      pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film, pl.B,
-      c.cond_channels, h->film_rows);
-  DMD_LAUNCH_OK();
+  {
+    const int total = pl.B * c.cond_channels;
+    cond_embed_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.cs, act, h->ptrs[h->i_fourier], h->ptrs[h->i_actemb], pl.cemb,
+                                                           pl.B, c.cond_channels, c.num_steps_conditioning, c.num_actions);
+    DMD_LAUNCH_OK();
+  }
+  if (linear_launch(pl.cemb, h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b], pl.chid, pl.B, c.cond_channels, c.cond_channels, 1, st)) return 1;
+  if (linear_launch(pl.chid, h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, pl.B, c.cond_channels, c.cond_channels, 0, st)) return 1;
+  if (linear_launch(pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film,
+                    pl.B, c.cond_channels, h->film_rows, 0, st)) return 1;
   for (const Op& op : pl.ops) {
     if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
@@ -487,7 +516,7 @@ int ensure_plan(dmd_denoiser* h, int B, int H, int W, void* ws, size_t ws_bytes)
 
 extern "C" dmd_denoiser* dmd_denoiser_create(const dmd_denoiser_config* cfg) {
   if (!cfg || cfg->num_levels < 1 || cfg->num_levels > DMD_MAX_LEVELS) { fail("denoiser_create: bad config"); return nullptr; }
-  if (cfg->cond_channels % 32 || cfg->cond_channels > 1024 || cfg->cond_channels % cfg->num_steps_conditioning) { fail("denoiser_create: cond_channels must be a multiple of 32 and of num_steps_conditioning"); return nullptr; }
+  if (cfg->cond_channels % 32 || cfg->cond_channels > 256 || cfg->cond_channels % cfg->num_steps_conditioning) { fail("denoiser_create: cond_channels must be a multiple of 32 (<= 256) and of num_steps_conditioning"); return nullptr; }
   for (int i = 0; i < cfg->num_levels; ++i)
     if (cfg->channels[i] % 32 || cfg->channels[i] > 64) { fail("denoiser_create: channels must be 32 or 64 per level (got %d)", cfg->channels[i]); return nullptr; }
   if (init_kernels()) return nullptr;

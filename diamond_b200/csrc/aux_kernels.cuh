@@ -65,79 +65,74 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// cond = cond_proj(noise_emb(c_noise) + act_emb(act))            (inner_model.py:45, :27-35, blocks.py:84-87)
-// one CTA per sample, CC = cond channels (multiple of 32, <= 1024), T conditioning steps, E = CC / T
-__global__ void cond_kernel(const float* __restrict__ cs, const int64_t* __restrict__ act, const float* __restrict__ fourier_w,
-                            const float* __restrict__ act_emb, const float* __restrict__ w0, const float* __restrict__ b0,
-                            const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ cond, int CC,
-                            int T, int num_actions) {
-  extern __shared__ float sm_cond[];
-  float* e0 = sm_cond;       // [CC]
-  float* e1 = sm_cond + CC;  // [CC]
-  const int n = blockIdx.x;
-  const float c_noise = cs[n * 4 + 3];
+// Conditioning path (inner_model.py:45, :27-35; blocks.py:84-87, :39,44), as one embedding kernel + three calls of a
+// small GEMM:   e = fourier(c_noise) + flatten(act_emb(act)) ;  h = silu(W0 e + b0) ;  cond = W1 h + b1 ;
+//               film = Wf cond + bf   (ALL AdaGroupNorm linears of the network batched: Wf = [sum 2C][CC])
+__global__ void cond_embed_kernel(const float* __restrict__ cs, const int64_t* __restrict__ act,
+                                  const float* __restrict__ fourier_w, const float* __restrict__ act_emb,
+                                  float* __restrict__ e, int B, int CC, int T, int num_actions) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * CC) return;
+  const int n = i / CC, k = i - n * CC;
   const int half = CC / 2, E = CC / T;
-  for (int k = threadIdx.x; k < CC; k += blockDim.x) {
-    const float t = __fmul_rn(6.283185307179586f, c_noise);
-    const float f = __fmul_rn(t, fourier_w[k < half ? k : k - half]);
-    const float four = k < half ? cosf(f) : sinf(f);
-    long long a = act[(size_t)n * T + k / E];
-    a = a < 0 ? 0 : (a >= num_actions ? num_actions - 1 : a);
-    e0[k] = __fadd_rn(four, act_emb[(size_t)a * E + (k % E)]);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < CC; o += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < CC; k += 32) acc = fmaf(w0[(size_t)o * CC + k], e0[k], acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      const float v = acc + b0[o];
-      e1[o] = v / (1.0f + expf(-v));
-    }
-  }
-  __syncthreads();
-  for (int o = warp; o < CC; o += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < CC; k += 32) acc = fmaf(w1[(size_t)o * CC + k], e1[k], acc);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) cond[(size_t)n * CC + o] = acc + b1[o];
-  }
+  const float c_noise = cs[n * 4 + 3];
+  const float t = __fmul_rn(6.283185307179586f, c_noise);
+  const float f = __fmul_rn(t, fourier_w[k < half ? k : k - half]);
+  const float four = k < half ? cosf(f) : sinf(f);
+  long long a = act[(size_t)n * T + k / E];
+  a = a < 0 ? 0 : (a >= num_actions ? num_actions - 1 : a);
+  e[i] = __fadd_rn(four, act_emb[(size_t)a * E + (k % E)]);
 }
 
-// All AdaGroupNorm linears of the network batched into ONE GEMM: film[n][f] = cond[n] . Wf[f] + bf[f]
-// (blocks.py:39,44).  Wf: [F][CC] rows = concatenation of every norm{1,2}.linear.weight in plan order.
-// grid: (ceil(F/64), ceil(B/32)), block 256.  Each warp owns 8 rows f, each lane one sample n.
-__global__ void film_kernel(const float* __restrict__ cond, const float* __restrict__ wf, const float* __restrict__ bf,
-                            float* __restrict__ film, int B, int CC, int F) {
-  extern __shared__ float condT[];  // [CC][32]
-  const int n0 = blockIdx.y * 32;
-  for (int i = threadIdx.x; i < CC * 32; i += blockDim.x) {
-    const int nn = i / CC, k = i - nn * CC;
-    condT[k * 32 + nn] = (n0 + nn < B) ? cond[(size_t)(n0 + nn) * CC + k] : 0.f;
+// out[n][f] = act( sum_k in[n][k] * W[f][k] + b[f] ),  K multiple of 4 and <= 256.
+// grid (ceil(F/32), ceil(B/32)), 256 threads: warp w owns rows f = 4w..4w+3 of the 32-row tile, lane = sample n.
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                     const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                     int K, int F, int silu) {
+  extern __shared__ __align__(16) float sm_lin[];
+  float* Ws = sm_lin;            // [32][K]
+  float* inT = sm_lin + 32 * K;  // [K][32]
+  const int f0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tid = threadIdx.x;
+  const int K4 = K >> 2;
+  for (int i = tid; i < 32 * K4; i += 256) {
+    const int r = i / K4, c4 = i - r * K4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f0 + r < F) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(f0 + r) * K) + c4);
+    reinterpret_cast<float4*>(Ws + r * K)[c4] = v;
+  }
+  for (int i = tid; i < 32 * K; i += 256) {
+    const int nn = i / K, k = i - nn * K;
+    inT[k * 32 + nn] = (n0 + nn < B) ? in[(size_t)(n0 + nn) * K + k] : 0.f;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = 0; r < 8; ++r) {
-    const int f = blockIdx.x * 64 + warp * 8 + r;
-    if (f >= F) break;
-    const float4* w = reinterpret_cast<const float4*>(wf + (size_t)f * CC);
-    float acc = 0.f;
-    for (int k4 = 0; k4 < CC / 4; ++k4) {
-      const float4 wv = __ldg(w + k4);
-      acc = fmaf(wv.x, condT[(k4 * 4 + 0) * 32 + lane], acc);
-      acc = fmaf(wv.y, condT[(k4 * 4 + 1) * 32 + lane], acc);
-      acc = fmaf(wv.z, condT[(k4 * 4 + 2) * 32 + lane], acc);
-      acc = fmaf(wv.w, condT[(k4 * 4 + 3) * 32 + lane], acc);
+  const int warp = tid >> 5, lane = tid & 31;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k4 = 0; k4 < K4; ++k4) {
+    const float x0 = inT[(4 * k4 + 0) * 32 + lane], x1 = inT[(4 * k4 + 1) * 32 + lane];
+    const float x2 = inT[(4 * k4 + 2) * 32 + lane], x3 = inT[(4 * k4 + 3) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = reinterpret_cast<const float4*>(Ws + (warp * 4 + j) * K)[k4];
+      acc[j] = fmaf(w.x, x0, acc[j]); acc[j] = fmaf(w.y, x1, acc[j]);
+      acc[j] = fmaf(w.z, x2, acc[j]); acc[j] = fmaf(w.w, x3, acc[j]);
     }
-    if (n0 + lane < B) film[(size_t)(n0 + lane) * F + f] = acc + bf[f];
+  }
+  if (n0 + lane < B) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = f0 + warp * 4 + j;
+      if (f < F) {
+        float v = acc[j] + bias[f];
+        if (silu) v = v / (1.0f + expf(-v));
+        out[(size_t)(n0 + lane) * F + f] = v;
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// SelfAttention2d (blocks.py:51-72), one CTA (256 threads) per image, L = H*W <= 64 tokens, C <= 64, head_dim 8.
+// SelfAttention2d (blocks.py:51-72), one CTA (512 threads) per image, L = 64 tokens, C in {32, 64}, head_dim 8.
 //   xn = GroupNorm(x) ; qkv = 1x1 ; att = softmax(q k^T / sqrt(d)) ; y = att v ; out = xn + out_proj(y)
 // NOTE the residual is added to the NORMED x (blocks.py:64 rebinding, :72).  Input stats come from the producer's
 // epilogue; output stats (for the next AdaGroupNorm) are accumulated here.
@@ -156,17 +151,20 @@ struct AttnParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(256) attn_kernel(const AttnParams p) {
-  extern __shared__ float sm_attn[];
-  const int L = p.L, C = p.C, C3 = 3 * C;
-  const int XP = C + 1, QP = C3 + 1;
-  float* xs = sm_attn;          // [L][C+1]   normed x
-  float* qkv = xs + L * XP;     // [L][3C+1]
-  float* ys = qkv + L * QP;     // [L][C+1]
+constexpr int kAttnThreads = 512;
+constexpr int kAttnL = 64;
+
+template <int C>
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnParams p) {
+  constexpr int L = kAttnL, C3 = 3 * C, XP = C + 1, QP = C3 + 4, HEADS = C / 8;
+  extern __shared__ __align__(16) float sm_attn[];
+  float* xs = sm_attn;          // [L][XP]   normed x
+  float* qkv = xs + L * XP;     // [L][QP]   (QP*4 bytes is a multiple of 16: rows are float4-addressable)
+  float* ys = qkv + L * QP;     // [L][XP]
   const int n = blockIdx.x, tid = threadIdx.x;
   const int G = C / p.gs;
   const float* xg = p.x + (size_t)n * L * C;
-  for (int i = tid; i < L * C; i += 256) {
+  for (int i = tid; i < L * C; i += kAttnThreads) {
     const int l = i / C, c = i - l * C;
     const int g = c / p.gs;
     const double cnt = (double)L * p.gs;
@@ -177,64 +175,95 @@ __global__ void __launch_bounds__(256) attn_kernel(const AttnParams p) {
     xs[l * XP + c] = (xg[i] - (float)mean) * rstd * p.gamma[c] + p.beta[c];
   }
   __syncthreads();
-  // qkv projection: item = (l, o) ; consecutive threads -> consecutive l (same o => weight row broadcast)
-  for (int i = tid; i < L * C3; i += 256) {
-    const int o = i / L, l = i - o * L;
-    const float* w = p.wqkv + (size_t)o * C;
-    float acc = p.bqkv[o];
-    for (int c = 0; c < C; ++c) acc = fmaf(xs[l * XP + c], __ldg(w + c), acc);
-    qkv[l * QP + o] = acc;
+  // ---- qkv projection.  thread = (token l, output group og of NO outputs); warp = 32 tokens, one og (weights broadcast)
+  {
+    constexpr int NG = kAttnThreads / L;  // 8 output groups
+    constexpr int NO = C3 / NG;           // 24 (C=64) or 12 (C=32) outputs per thread
+    const int l = tid % L, og = tid / L;
+    float acc[NO];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) acc[i] = __ldg(p.bqkv + og * NO + i);
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float x0 = xs[l * XP + 4 * c4], x1 = xs[l * XP + 4 * c4 + 1], x2 = xs[l * XP + 4 * c4 + 2], x3 = xs[l * XP + 4 * c4 + 3];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wqkv + (size_t)(og * NO + i) * C) + c4);
+        acc[i] = fmaf(w.x, x0, acc[i]); acc[i] = fmaf(w.y, x1, acc[i]);
+        acc[i] = fmaf(w.z, x2, acc[i]); acc[i] = fmaf(w.w, x3, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NO; ++i) qkv[l * QP + og * NO + i] = acc[i];
   }
   __syncthreads();
-  // attention: item = (head h, query l)
-  const int heads = C / 8;
-  const float inv_sqrt_d = 0.35355339059327373f;  // 1/sqrt(8)
-  for (int i = tid; i < heads * L; i += 256) {
-    const int h = i / L, l = i - h * L;
+  // ---- attention: item = (head h, query l); K/V rows are warp-broadcast float4 reads
+  for (int it = tid; it < HEADS * L; it += kAttnThreads) {
+    const int h = it / L, l = it - h * L;
     float q[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) q[e] = qkv[l * QP + h * 8 + e];
-    float sc[64];
+    for (int e = 0; e < 8; ++e) q[e] = qkv[l * QP + h * 8 + e] * 0.35355339059327373f;  // 1/sqrt(8)
+    float sc[L];
     float mx = -INFINITY;
-    for (int j = 0; j < L; ++j) {
-      float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s = fmaf(q[e], qkv[j * QP + C + h * 8 + e], s);
-      s *= inv_sqrt_d;
-      sc[j] = s;
-      mx = fmaxf(mx, s);
+    for (int j = 0; j < L; ++j) {
+      const float4 k0 = *reinterpret_cast<const float4*>(qkv + j * QP + C + h * 8);
+      const float4 k1 = *reinterpret_cast<const float4*>(qkv + j * QP + C + h * 8 + 4);
+      float sj = q[0] * k0.x;
+      sj = fmaf(q[1], k0.y, sj); sj = fmaf(q[2], k0.z, sj); sj = fmaf(q[3], k0.w, sj);
+      sj = fmaf(q[4], k1.x, sj); sj = fmaf(q[5], k1.y, sj); sj = fmaf(q[6], k1.z, sj); sj = fmaf(q[7], k1.w, sj);
+      sc[j] = sj;
+      mx = fmaxf(mx, sj);
     }
     float den = 0.f;
+#pragma unroll
     for (int j = 0; j < L; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
     const float inv = 1.0f / den;
     float y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = 0; j < L; ++j) {
-      const float pj = sc[j] * inv;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = fmaf(pj, qkv[j * QP + 2 * C + h * 8 + e], y[e]);
+    for (int j = 0; j < L; ++j) {
+      const float4 v0 = *reinterpret_cast<const float4*>(qkv + j * QP + 2 * C + h * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(qkv + j * QP + 2 * C + h * 8 + 4);
+      const float pj = sc[j] * inv;
+      y[0] = fmaf(pj, v0.x, y[0]); y[1] = fmaf(pj, v0.y, y[1]); y[2] = fmaf(pj, v0.z, y[2]); y[3] = fmaf(pj, v0.w, y[3]);
+      y[4] = fmaf(pj, v1.x, y[4]); y[5] = fmaf(pj, v1.y, y[5]); y[6] = fmaf(pj, v1.z, y[6]); y[7] = fmaf(pj, v1.w, y[7]);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) ys[l * XP + h * 8 + e] = y[e];
   }
   __syncthreads();
-  // out projection + residual on normed x; stats of the output per group
-  float* og = p.out + (size_t)n * L * C;
-  for (int i = tid; i < L * C; i += 256) {
-    const int o = i / L, l = i - o * L;  // warp = 32 consecutive l, one o
-    const float* w = p.wout + (size_t)o * C;
-    float acc = p.bout[o];
-    for (int c = 0; c < C; ++c) acc = fmaf(ys[l * XP + c], __ldg(w + c), acc);
-    const float v = xs[l * XP + o] + acc;
-    og[(size_t)l * C + o] = v;
+  // ---- out projection + residual on normed x; output statistics.  thread = (token l, NO2 outputs)
+  {
+    constexpr int NG = kAttnThreads / L;  // 8
+    constexpr int NO2 = C / NG;           // 8 or 4 consecutive outputs: always inside one GroupNorm group
+    const int l = tid % L, og = tid / L;
+    float acc[NO2];
+#pragma unroll
+    for (int i = 0; i < NO2; ++i) acc[i] = __ldg(p.bout + og * NO2 + i);
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float y0 = ys[l * XP + 4 * c4], y1 = ys[l * XP + 4 * c4 + 1], y2 = ys[l * XP + 4 * c4 + 2], y3 = ys[l * XP + 4 * c4 + 3];
+#pragma unroll
+      for (int i = 0; i < NO2; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wout + (size_t)(og * NO2 + i) * C) + c4);
+        acc[i] = fmaf(w.x, y0, acc[i]); acc[i] = fmaf(w.y, y1, acc[i]);
+        acc[i] = fmaf(w.z, y2, acc[i]); acc[i] = fmaf(w.w, y3, acc[i]);
+      }
+    }
+    float* og_ptr = p.out + (size_t)n * L * C + (size_t)l * C + og * NO2;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < NO2; ++i) {
+      const float v = xs[l * XP + og * NO2 + i] + acc[i];
+      og_ptr[i] = v;
+      a += v; b += v * v;
+    }
     if (p.ostats) {
-      float a = v, b = v * v;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, off);
         b += __shfl_xor_sync(0xffffffffu, b, off);
       }
       if ((tid & 31) == 0) {
-        const int g = o / p.gs;
+        const int g = (og * NO2) / p.gs;
         atomicAdd(p.ostats + ((size_t)n * G + g) * 2, (double)a);
         atomicAdd(p.ostats + ((size_t)n * G + g) * 2 + 1, (double)b);
       }

@@ -1,4 +1,4 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC fp32 activations.
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC fp32 activations.  Persistent + warp-specialised.
 //
 // Replaces, on the hot path, every nn.Conv2d of the reference (blocks.py:18-19 Conv1x1/Conv3x3, :96 Downsample,
 // :109-110 Upsample, inner_model.py:36,41 conv_in/conv_out) together with what the reference runs around it:
@@ -8,23 +8,35 @@
 //              the NEXT GroupNorm over the conv OUTPUT.
 //
 // Geometry ("padded-linear" implicit GEMM).  Pixels of all B images are laid out on one line with pitch
-// PW = W+1 and PH = H+1 rows per image: q = (n*PH + y)*PW + x.  Column x==W and row y==H are zero padding that is
-// shared between neighbouring rows / images, so tap (dy,dx) of a 3x3 window is simply position q + dy*PW + dx.
-// A CTA owns 128 consecutive q (the MMA M dimension).  It stages the normalised fp16 "halo" [q0-PW-1, q0+128+PW+1)
-// ONCE into shared memory in the UMMA no-swizzle K-major layout  [channel-chunk j][position p][8 ch = 16 B],
-// and each of the 9 taps x (Cin/16) MMAs reads the same halo through a descriptor whose start address is shifted by
-// (dy*PW+dx) positions * 16 B.  Weights are pre-packed on the host side of the C-ABI as [tap][Cin/8][CoutPad][8] fp16
-// (the same canonical layout for the B operand) and arrive with one bulk async copy per tap.
-// Accumulators (128 x CoutPad fp32) live in TMEM; the epilogue reads them back with tcgen05.ld.
+// PW = W+1 and PH = H+1 rows per image: q = (n*PH + y)*PW + x.  Column x==W and row y==H are zero padding shared
+// between neighbouring rows / images, so tap (dy,dx) of a 3x3 window is simply position q + dy*PW + dx.
+// A tile is 128 consecutive q (the MMA M dimension).  Its normalised fp16 halo [q0-PW-1, q0+128+PW+1) is staged ONCE
+// in shared memory in the UMMA no-swizzle K-major layout, one "slab" per 16 input channels:
+//     slab = [2 chunks of 8 channels][P positions][16 B]          (LBO = Palloc*16, SBO = 128)
+// and every tap reads the same slab through a descriptor whose start address is shifted by (dy*PW+dx)*16 B.
+//
+// Roles (416 threads, one CTA per SM, tiles strided over the grid):
+//   warps 0-7   loaders : global fp32 -> GN/FiLM affine -> SiLU -> fp16 -> slab ring (full/empty mbarriers)
+//   warp  8     MMA     : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap); tcgen05.commit frees
+//                         the slab and, after the last slab, publishes the TMEM accumulator
+//   warps 9-12  epilogue: tcgen05.ld accumulator rows, + bias + residual, store NHWC, GroupNorm partial sums
+// Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
+// TMEM holds two accumulators so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #pragma once
 #include "ptx.cuh"
 
 namespace dmd {
 
-constexpr int kConvThreads = 256;
+constexpr int kLoadWarps = 8;
+constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kMmaWarp = kLoadWarps;           // warp 8
+constexpr int kEpiWarp0 = kLoadWarps + 1;      // warps 9..12
+constexpr int kConvThreads = (kLoadWarps + 5) * 32;  // 416
 constexpr int kTileM = 128;
 constexpr int kMaxImgSlots = 4;
 constexpr int kMaxCin = 128;
+constexpr int kMaxStages = 16;
+constexpr int kMaxPosPerThread = 4;  // ceil(P / 128) with P <= 512
 
 struct FastDiv {
   uint32_t d, m;
@@ -70,270 +82,321 @@ struct ConvParams {
   // derived (host fills)
   int PW, PH, Q;      // pitch, rows per image, total positions B*PH*PW
   int P, Palloc;      // halo positions, odd allocation pitch
+  int num_tiles, stages;
   FastDiv dPW, dPH;
-  int dbg;            // bit0: swap LBO/SBO (bring-up probe only)
+  int dbg;
 };
 
 struct ConvSmemLayout {
-  uint32_t coef_off, w_off, a_off, total;
+  uint32_t coef_off, w_off, a_off, slab_bytes, total;
 };
 
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc) {
+// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], tmem slot
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
-  L.coef_off = 64;  // [0,64): mbarriers + tmem pointer
-  uint32_t coef_bytes = kMaxImgSlots * kMaxCin * 2 * sizeof(float);
+  L.coef_off = 512;
+  const uint32_t coef_bytes = 2u * kMaxImgSlots * kMaxCin * 2 * sizeof(float);  // two parities x (a, b)
   L.w_off = (L.coef_off + coef_bytes + 127u) & ~127u;
-  uint32_t w_bytes = (uint32_t)taps * Cin * CoutPad * 2;
+  const uint32_t w_bytes = (uint32_t)taps * Cin * CoutPad * 2;
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
-  uint32_t a_bytes = (uint32_t)(Cin / 8) * Palloc * 16;
-  L.total = L.a_off + a_bytes + 16;
+  L.slab_bytes = 2u * Palloc * 16;
+  L.total = L.a_off + (uint32_t)stages * L.slab_bytes + 16;
   return L;
 }
 
-template <int kTmemCols>
-__global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const ConvParams p) {
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int kAccCols>  // TMEM columns per accumulator (>= CoutPad); two accumulators are allocated
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);        // weights landed
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 8);    // MMAs retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
-  const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc);
-  float* coefA = reinterpret_cast<float*>(smem + L.coef_off);
-  float* coefB = coefA + kMaxImgSlots * kMaxCin;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* full = wbar + 1;                 // [kMaxStages]
+  uint64_t* empty = full + kMaxStages;       // [kMaxStages]
+  uint64_t* tfull = empty + kMaxStages;      // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc, p.stages);
+  float* coef = reinterpret_cast<float*>(smem + L.coef_off);  // [parity][a|b][slot][kMaxCin]
   uint8_t* sW = smem + L.w_off;
   uint8_t* sA = smem + L.a_off;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * kTileM;
   const int halo = (p.taps == 9) ? (p.PW + 1) : 0;
-  const int qh0 = q0 - halo;  // first halo position (may be negative)
   const int Ctot = p.C0 + p.C1;
-  const uint32_t img_sz = (uint32_t)p.PH * p.PW;
-  const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+  const int S = p.stages;
+  const int kslabs = p.Cin >> 4;
 
-  // ---- setup: barriers, weight bulk copy, TMEM allocation
+  // ---- setup
   if (tid == 0) {
     mbar_init(wbar, 1);
-    mbar_init(mbar, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, kLoadWarps); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     mbar_expect_tx(wbar, tap_bytes * p.taps);
     for (int t = 0; t < p.taps; ++t)
-      bulk_g2s(sW + (size_t)t * tap_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)t * tap_bytes, tap_bytes,
-               wbar);
+      bulk_g2s(sW + (size_t)t * tap_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)t * tap_bytes, tap_bytes, wbar);
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
-
-  // ---- per-(image, channel) prologue coefficients  y = act(a*x + b)
-  if (p.pro != 0) {
-    for (int i = tid; i < kMaxImgSlots * Ctot; i += kConvThreads) {
-      const int slot = i / Ctot, c = i - slot * Ctot;
-      const int n = n_first + slot;
-      float a = 0.f, b = 0.f;
-      if (n < p.B) {
-        const double* st;
-        int g, gs, G;
-        if (c < p.C0) { gs = p.gs0; G = p.C0 / gs; g = c / gs; st = p.st0 + ((size_t)n * G + g) * 2; }
-        else { gs = p.gs1; G = p.C1 / gs; g = (c - p.C0) / gs; st = p.st1 + ((size_t)n * G + g) * 2; }
-        const double cnt = (double)p.Hs * p.Ws * gs;
-        const double mean = st[0] / cnt;
-        double var = st[1] / cnt - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-        float sc, sh;
-        if (p.pro == 1) {
-          const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
-          sc = 1.f + f[c];
-          sh = f[Ctot + c];
-        } else {
-          sc = p.gamma[c];
-          sh = p.beta[c];
-        }
-        a = rstd * sc;
-        b = sh - (float)mean * a;
-      }
-      coefA[slot * kMaxCin + c] = a;
-      coefB[slot * kMaxCin + c] = b;
-    }
-  }
+  if (warp == kMmaWarp) tmem_alloc<2 * kAccCols>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- stage the halo:  thread owns channel chunk j (8 channels) for positions pp, pp+pstep, ...
-  {
-    const int nch = p.Cin >> 3;
-    const int pstep = kConvThreads / nch;
-    const int j = tid % nch;
-    int pp = tid / nch;
-    if (pp < pstep) {
-      const int cbase = j * 8;
-      const float* src = nullptr;
-      int Csrc = 0, coff = 0;
-      if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
-      else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
-      float ca[8], cb[8];
-      int cur_slot = -1;
-      uint8_t* dstj = sA + (size_t)j * p.Palloc * 16;
-      for (; pp < p.P; pp += pstep) {
+  if (warp < kLoadWarps) {
+    // =========================================================================================== LOADERS
+    uint32_t g = 0;  // slab counter across tiles
+    const int sub = tid & 1;   // which 8-channel chunk of the slab
+    const int pos0 = tid >> 1; // first owned halo position; then += 128
+    for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+      const int q0 = tile * kTileM;
+      const int qh0 = q0 - halo;
+      const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+      float* cA = coef + (size_t)(it & 1) * (2 * kMaxImgSlots * kMaxCin);
+      float* cB = cA + kMaxImgSlots * kMaxCin;
+      if (p.pro != 0) {
+        for (int i = tid; i < kMaxImgSlots * Ctot; i += kLoadThreads) {
+          const int slot = i / Ctot, c = i - slot * Ctot;
+          const int n = n_first + slot;
+          float a = 0.f, b = 0.f;
+          if (n < p.B) {
+            const double* st;
+            int gs;
+            if (c < p.C0) { gs = p.gs0; st = p.st0 + ((size_t)n * (p.C0 / gs) + c / gs) * 2; }
+            else { gs = p.gs1; st = p.st1 + ((size_t)n * (p.C1 / gs) + (c - p.C0) / gs) * 2; }
+            const double cnt = (double)p.Hs * p.Ws * gs;
+            const double mean = st[0] / cnt;
+            double var = st[1] / cnt - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+            float sc, sh;
+            if (p.pro == 1) {
+              const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
+              sc = 1.f + __ldg(f + c);
+              sh = __ldg(f + Ctot + c);
+            } else {
+              sc = __ldg(p.gamma + c);
+              sh = __ldg(p.beta + c);
+            }
+            a = rstd * sc;
+            b = sh - (float)mean * a;
+          }
+          cA[slot * kMaxCin + c] = a;
+          cB[slot * kMaxCin + c] = b;
+        }
+        named_bar_sync(1, kLoadThreads);
+      }
+      // decode owned positions once per tile: pixel index into the source (or -1 => zero) and image slot
+      int pix[kMaxPosPerThread], slot[kMaxPosPerThread];
+#pragma unroll
+      for (int k = 0; k < kMaxPosPerThread; ++k) {
+        pix[k] = -1; slot[k] = 0;
+        const int pp = pos0 + k * 128;
         const int q = qh0 + pp;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (src != nullptr && q >= 0 && q < p.Q) {
+        if (pp < p.P && q >= 0 && q < p.Q) {
           const uint32_t R = p.dPW.div((uint32_t)q);
           const int x = q - (int)R * p.PW;
           const uint32_t n = p.dPH.div(R);
           const int y = (int)R - (int)n * p.PH;
           if (x < p.W && y < p.H) {
             const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-            const float4* g = reinterpret_cast<const float4*>(src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * Csrc + coff);
-            const float4 v0 = __ldg(g), v1 = __ldg(g + 1);
-            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            if (p.pro != 0) {
-              const int slot = (int)n - n_first;
-              if (slot != cur_slot) {
-                cur_slot = slot;
+            pix[k] = ((int)n * p.Hs + ys) * p.Ws + xs;
+            slot[k] = (int)n - n_first;
+          }
+        }
+      }
+      const int npos = (p.P + 127) >> 7;  // passes needed (<= kMaxPosPerThread)
+      for (int ks = 0; ks < kslabs; ++ks, ++g) {
+        const int cbase = ks * 16 + sub * 8;
+        const float* src = nullptr;
+        int Csrc = 0, coff = 0;
+        if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
+        else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
+        // issue every load of this slab first (memory-level parallelism), then wait for the ring slot
+        float4 v0[kMaxPosPerThread], v1[kMaxPosPerThread];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  ca[i] = coefA[slot * kMaxCin + cbase + i];
-                  cb[i] = coefB[slot * kMaxCin + cbase + i];
+        for (int k = 0; k < kMaxPosPerThread; ++k) {
+          v0[k] = make_float4(0.f, 0.f, 0.f, 0.f); v1[k] = v0[k];
+          if (k < npos && src != nullptr && pix[k] >= 0) {
+            const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[k] * Csrc + coff);
+            v0[k] = __ldg(gp); v1[k] = __ldg(gp + 1);
+          }
+        }
+        const int stage = (int)(g % (uint32_t)S);
+        const uint32_t ph = (g / (uint32_t)S) & 1u;
+        mbar_wait(empty + stage, ph ^ 1u);
+        uint8_t* dst = sA + (size_t)stage * L.slab_bytes + (size_t)sub * p.Palloc * 16;
+#pragma unroll
+        for (int k = 0; k < kMaxPosPerThread; ++k) {
+          const int pp = pos0 + k * 128;
+          if (k < npos && pp < p.P) {
+            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+            if (src != nullptr && pix[k] >= 0) {
+              float v[8] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
+              if (p.pro != 0) {
+                const float4* ca = reinterpret_cast<const float4*>(cA + slot[k] * kMaxCin + cbase);
+                const float4* cb = reinterpret_cast<const float4*>(cB + slot[k] * kMaxCin + cbase);
+                const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
+                v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
+                v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
+              }
+              if (p.act) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+              }
+              packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
+              packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = packed;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + stage);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================================================================================== MMA ISSUER
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
+      const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
+      const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
+      const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
+      uint32_t g = 0;
+      for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+        const int b = it & 1;
+        mbar_wait(tempty + b, (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
+        uint32_t acc = 0;
+        for (int ks = 0; ks < kslabs; ++ks, ++g) {
+          const int stage = (int)(g % (uint32_t)S);
+          mbar_wait(full + stage, (g / (uint32_t)S) & 1u);
+          tc_fence_after_sync();
+          const uint32_t slab = a_base + (uint32_t)stage * L.slab_bytes;
+          for (int t = 0; t < p.taps; ++t) {
+            int shift = halo;
+            if (p.taps == 9) shift += (t / 3 - 1) * p.PW + (t % 3 - 1);
+            const uint64_t ad = umma_desc(slab + (uint32_t)shift * 16, a_lbo, 128);
+            const uint64_t bd = umma_desc(w_base + (uint32_t)t * tap_bytes + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+            umma_f16(d_tmem, ad, bd, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(empty + stage);  // slab reusable once these MMAs retire
+        }
+        umma_commit(tfull + b);        // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================================== EPILOGUE
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int nchunks = p.CoutPad >> 4;
+    const bool vec_ok = (p.Cout & 3) == 0;
+    const int G = p.ostats ? p.Cout / p.ogs : 1;
+    for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+      const int b = it & 1;
+      const int q = tile * kTileM + quarter * 32 + lane;
+      bool valid = false;
+      int n = p.B;  // out-of-range rows belong to no image
+      size_t opix = 0;
+      if (q < p.Q) {
+        const uint32_t R = p.dPW.div((uint32_t)q);
+        const int x = q - (int)R * p.PW;
+        n = (int)p.dPH.div(R);
+        const int y = (int)R - n * p.PH;
+        valid = (x < p.W) && (y < p.H);
+        int yo = y, xo = x, Ho = p.H, Wo = p.W;
+        if (p.stride == 2) {
+          valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
+          yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+        }
+        opix = ((size_t)n * Ho + yo) * Wo + xo;
+      }
+      const int n_lo = __shfl_sync(0xffffffffu, n, 0), n_hi = __shfl_sync(0xffffffffu, n, 31);
+      float* orow = p.out + opix * p.Cout;
+      const float* rrow = p.resid ? p.resid + opix * p.Cout : nullptr;
+      // prefetch the residual of the first chunk while the MMAs are still running
+      float4 rnext[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && rrow && vec_ok && 16 <= p.Cout) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow) + i);
+      }
+      mbar_wait(tfull + b, ((uint32_t)it >> 1) & 1u);
+      tc_fence_after_sync();
+      const uint32_t trow = tmem_base + (uint32_t)b * kAccCols + ((uint32_t)(quarter * 32) << 16);
+      float s = 0.f, ss = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)ch * 16, v);
+        const int c0 = ch * 16;
+        float4 rcur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { rcur[i] = rnext[i]; rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        if (valid && rrow && vec_ok && c0 + 32 <= p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + i);
+        }
+        if (valid) {
+          if (vec_ok && c0 + 16 <= p.Cout) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0) + i) : make_float4(0, 0, 0, 0);
+              v[4 * i + 0] += bv.x + rcur[i].x; v[4 * i + 1] += bv.y + rcur[i].y;
+              v[4 * i + 2] += bv.z + rcur[i].z; v[4 * i + 3] += bv.w + rcur[i].w;
+              *reinterpret_cast<float4*>(orow + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (c0 + i < p.Cout) {
+                v[i] += (p.bias ? __ldg(p.bias + c0 + i) : 0.f) + (rrow ? __ldg(rrow + c0 + i) : 0.f);
+                orow[c0 + i] = v[i];
+              } else {
+                v[i] = 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s += v[i]; ss += v[i] * v[i]; }
+        }
+        if (p.ostats != nullptr) {  // flush GroupNorm partials at a group boundary
+          const int cnext = c0 + 16;
+          if ((cnext % p.ogs) == 0 || cnext >= p.Cout) {
+            const int grp = c0 / p.ogs;
+            if (grp < G) {
+              for (int img = n_lo; img <= n_hi; ++img) {
+                if (img >= p.B) continue;
+                float a = (valid && n == img) ? s : 0.f, bq = (valid && n == img) ? ss : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                  a += __shfl_xor_sync(0xffffffffu, a, off);
+                  bq += __shfl_xor_sync(0xffffffffu, bq, off);
+                }
+                if (lane == 0) {
+                  atomicAdd(p.ostats + ((size_t)img * G + grp) * 2, (double)a);
+                  atomicAdd(p.ostats + ((size_t)img * G + grp) * 2 + 1, (double)bq);
                 }
               }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaf(ca[i], v[i], cb[i]);
             }
-            if (p.act) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-            }
-            packed.x = pack_h2(v[0], v[1]);
-            packed.y = pack_h2(v[2], v[3]);
-            packed.z = pack_h2(v[4], v[5]);
-            packed.w = pack_h2(v[6], v[7]);
+            s = 0.f; ss = 0.f;
           }
         }
-        *reinterpret_cast<uint4*>(dstj + (size_t)pp * 16) = packed;
       }
-    }
-  }
-  fence_proxy_async_smem();
-  __syncthreads();
-
-  // ---- MMA issue (one thread)
-  if (tid == 0) {
-    mbar_wait(wbar, 0);
-    tc_fence_after_sync();
-    const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
-    const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
-    const uint32_t a_lbo = (uint32_t)p.Palloc * 16, a_sbo = 128;
-    const uint32_t b_lbo = (uint32_t)p.CoutPad * 16, b_sbo = 128;
-    const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
-    const int kblocks = p.Cin >> 4;
-    uint32_t acc = 0;
-    for (int t = 0; t < p.taps; ++t) {
-      int shift = halo;
-      if (p.taps == 9) shift += (t / 3 - 1) * p.PW + (t % 3 - 1);
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const uint32_t a_addr = a_base + (uint32_t)(2 * kb) * a_lbo + (uint32_t)shift * 16;
-        const uint32_t b_addr = w_base + (uint32_t)t * tap_bytes + (uint32_t)(2 * kb) * b_lbo;
-        uint64_t ad, bd;
-        if (p.dbg & 1) { ad = umma_desc(a_addr, a_sbo, a_lbo); bd = umma_desc(b_addr, b_sbo, b_lbo); }
-        else { ad = umma_desc(a_addr, a_lbo, a_sbo); bd = umma_desc(b_addr, b_lbo, b_sbo); }
-        umma_f16(tmem_base, ad, bd, idesc, acc);
-        acc = 1;
-      }
-    }
-    umma_commit(mbar);
-  }
-  __syncwarp();
-
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (= positions), column chunks split between w<4 / w>=4
-  mbar_wait(mbar, 0);
-  tc_fence_after_sync();
-  {
-    const int row = (warp & 3) * 32 + lane;
-    const int q = q0 + row;
-    bool valid = false;
-    int n = p.B;  // out-of-range rows belong to no image
-    size_t opix = 0;
-    if (q < p.Q) {
-      const uint32_t R = p.dPW.div((uint32_t)q);
-      const int x = q - (int)R * p.PW;
-      n = (int)p.dPH.div(R);
-      const int y = (int)R - n * p.PH;
-      valid = (x < p.W) && (y < p.H);
-      int yo = y, xo = x, Ho = p.H, Wo = p.W;
-      if (p.stride == 2) {
-        valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
-        yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
-      }
-      opix = ((size_t)n * Ho + yo) * Wo + xo;
-    }
-    const int nchunks = p.CoutPad >> 4;
-    const int half = (nchunks + 1) >> 1;
-    const int c_begin = (warp < 4) ? 0 : half, c_end = (warp < 4) ? half : nchunks;
-    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int n_lo = __shfl_sync(0xffffffffu, n, 0), n_hi = __shfl_sync(0xffffffffu, n, 31);
-    const bool vec_ok = (p.Cout & 3) == 0;
-    float s = 0.f, ss = 0.f;
-    for (int ch = c_begin; ch < c_end; ++ch) {
-      float v[16];
-      tmem_ld16(trow + (uint32_t)ch * 16, v);
-      const int c0 = ch * 16;
-      if (valid) {
-        float* o = p.out + opix * p.Cout + c0;
-        const float* r = p.resid ? p.resid + opix * p.Cout + c0 : nullptr;
-        if (vec_ok && c0 + 16 <= p.Cout) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)) : make_float4(0, 0, 0, 0);
-            float4 rv = r ? __ldg(reinterpret_cast<const float4*>(r + i)) : make_float4(0, 0, 0, 0);
-            v[i] += bv.x + rv.x; v[i + 1] += bv.y + rv.y; v[i + 2] += bv.z + rv.z; v[i + 3] += bv.w + rv.w;
-            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (c0 + i < p.Cout) {
-              v[i] += (p.bias ? __ldg(p.bias + c0 + i) : 0.f) + (r ? __ldg(r + i) : 0.f);
-              o[i] = v[i];
-            } else {
-              v[i] = 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { s += v[i]; ss += v[i] * v[i]; }
-      }
-      // flush GroupNorm partials at a group boundary
-      if (p.ostats != nullptr) {
-        const int cnext = c0 + 16;
-        if ((cnext % p.ogs) == 0 || cnext >= p.Cout || ch == c_end - 1) {
-          const int g = c0 / p.ogs;
-          const int G = p.Cout / p.ogs;
-          if (g < G) {
-            for (int img = n_lo; img <= n_hi; ++img) {
-              if (img >= p.B) continue;
-              float a = (valid && n == img) ? s : 0.f, b = (valid && n == img) ? ss : 0.f;
-#pragma unroll
-              for (int off = 16; off > 0; off >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, off);
-                b += __shfl_xor_sync(0xffffffffu, b, off);
-              }
-              if (lane == 0) {
-                atomicAdd(p.ostats + ((size_t)img * G + g) * 2, (double)a);
-                atomicAdd(p.ostats + ((size_t)img * G + g) * 2 + 1, (double)b);
-              }
-            }
-          }
-          s = 0.f; ss = 0.f;
-        }
-      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + b);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_free<kTmemCols>(tmem_base);
+  if (warp == kMmaWarp) tmem_free<2 * kAccCols>(tmem_base);
 }
 
 }  // namespace dmd
