@@ -20,6 +20,8 @@
 //   warp  8     MMA     : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap); tcgen05.commit frees
 //                         the slab and, after the last slab, publishes the TMEM accumulator
 //   warps 9-12  epilogue: tcgen05.ld accumulator rows, + bias + residual, store NHWC, GroupNorm partial sums
+//   warp  13    coef    : per-(image, channel) prologue coefficients a = rstd*(1+scale), b = shift - mean*a for the tile
+//                         AFTER the one being loaded (fp64 statistics -> fp32), double-buffered in shared memory
 // Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
 // TMEM holds two accumulators so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #pragma once
@@ -31,7 +33,8 @@ constexpr int kLoadWarps = 8;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMmaWarp = kLoadWarps;           // warp 8
 constexpr int kEpiWarp0 = kLoadWarps + 1;      // warps 9..12
-constexpr int kConvThreads = (kLoadWarps + 5) * 32;  // 416
+constexpr int kCoefWarp = kLoadWarps + 5;       // warp 13: GN/FiLM coefficients, one tile ahead of the loaders
+constexpr int kConvThreads = (kLoadWarps + 6) * 32;  // 448
 constexpr int kTileM = 128;
 constexpr int kMaxImgSlots = 4;
 constexpr int kMaxCin = 128;
@@ -91,7 +94,7 @@ struct ConvSmemLayout {
   uint32_t coef_off, w_off, a_off, slab_bytes, total;
 };
 
-// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], tmem slot
+// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], cfull[2], cempty[2], tmem slot
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
   L.coef_off = 512;
@@ -116,7 +119,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   uint64_t* empty = full + kMaxStages;       // [kMaxStages]
   uint64_t* tfull = empty + kMaxStages;      // [2]
   uint64_t* tempty = tfull + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* cfull = tempty + 2;              // [2] coefficient table ready
+  uint64_t* cempty = cfull + 2;              // [2] coefficient table consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
   const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc, p.stages);
   float* coef = reinterpret_cast<float*>(smem + L.coef_off);  // [parity][a|b][slot][kMaxCin]
   uint8_t* sW = smem + L.w_off;
@@ -133,7 +138,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, kLoadWarps); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1); mbar_init(tempty + b, 4);
+      mbar_init(cfull + b, 1); mbar_init(cempty + b, kLoadWarps);
+    }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     mbar_expect_tx(wbar, tap_bytes * p.taps);
@@ -148,55 +156,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
 
   if (warp < kLoadWarps) {
     // =========================================================================================== LOADERS
-    uint32_t g = 0;  // slab counter across tiles
-    const int sub = tid & 1;   // which 8-channel chunk of the slab
-    const int pos0 = tid >> 1; // first owned halo position; then += 128
-    for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
-      const int q0 = tile * kTileM;
+    // Software pipeline: the global loads of slab g+1 (possibly the first slab of the NEXT tile) are in flight while
+    // slab g is normalised and written to the ring.  Every thread owns halo positions pos0, pos0+128, ... and one of
+    // the two 8-channel chunks of each slab; per-tile pixel offsets are decoded once.
+    const int sub = tid & 1;
+    const int pos0 = tid >> 1;
+    const int npos = (p.P + 127) >> 7;  // passes needed (<= kMaxPosPerThread)
+    const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)kslabs;
+
+    // load cursor state
+    int l_it = 0, l_ks = 0;
+    int pix[kMaxPosPerThread];
+    uint32_t l_meta = 0;  // per position: bit (8k) valid, bits (8k+1..8k+2) image slot
+    auto decode_tile = [&](int it_) {
+      const int q0 = ((int)blockIdx.x + it_ * (int)gridDim.x) * kTileM;
       const int qh0 = q0 - halo;
       const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
-      float* cA = coef + (size_t)(it & 1) * (2 * kMaxImgSlots * kMaxCin);
-      float* cB = cA + kMaxImgSlots * kMaxCin;
-      if (p.pro != 0) {
-        for (int i = tid; i < kMaxImgSlots * Ctot; i += kLoadThreads) {
-          const int slot = i / Ctot, c = i - slot * Ctot;
-          const int n = n_first + slot;
-          float a = 0.f, b = 0.f;
-          if (n < p.B) {
-            const double* st;
-            int gs;
-            if (c < p.C0) { gs = p.gs0; st = p.st0 + ((size_t)n * (p.C0 / gs) + c / gs) * 2; }
-            else { gs = p.gs1; st = p.st1 + ((size_t)n * (p.C1 / gs) + (c - p.C0) / gs) * 2; }
-            const double cnt = (double)p.Hs * p.Ws * gs;
-            const double mean = st[0] / cnt;
-            double var = st[1] / cnt - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-            float sc, sh;
-            if (p.pro == 1) {
-              const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
-              sc = 1.f + __ldg(f + c);
-              sh = __ldg(f + Ctot + c);
-            } else {
-              sc = __ldg(p.gamma + c);
-              sh = __ldg(p.beta + c);
-            }
-            a = rstd * sc;
-            b = sh - (float)mean * a;
-          }
-          cA[slot * kMaxCin + c] = a;
-          cB[slot * kMaxCin + c] = b;
-        }
-        named_bar_sync(1, kLoadThreads);
-      }
-      // decode owned positions once per tile: pixel index into the source (or -1 => zero) and image slot
-      int pix[kMaxPosPerThread], slot[kMaxPosPerThread];
+      l_meta = 0;
 #pragma unroll
       for (int k = 0; k < kMaxPosPerThread; ++k) {
-        pix[k] = -1; slot[k] = 0;
+        pix[k] = -1;
         const int pp = pos0 + k * 128;
         const int q = qh0 + pp;
-        if (pp < p.P && q >= 0 && q < p.Q) {
+        if (k < npos && pp < p.P && q >= 0 && q < p.Q) {
           const uint32_t R = p.dPW.div((uint32_t)q);
           const int x = q - (int)R * p.PW;
           const uint32_t n = p.dPH.div(R);
@@ -204,58 +187,83 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           if (x < p.W && y < p.H) {
             const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
             pix[k] = ((int)n * p.Hs + ys) * p.Ws + xs;
-            slot[k] = (int)n - n_first;
+            l_meta |= (1u | ((uint32_t)((int)n - n_first) << 1)) << (8 * k);
           }
         }
       }
-      const int npos = (p.P + 127) >> 7;  // passes needed (<= kMaxPosPerThread)
-      for (int ks = 0; ks < kslabs; ++ks, ++g) {
-        const int cbase = ks * 16 + sub * 8;
-        const float* src = nullptr;
-        int Csrc = 0, coff = 0;
-        if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
-        else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
-        // issue every load of this slab first (memory-level parallelism), then wait for the ring slot
-        float4 v0[kMaxPosPerThread], v1[kMaxPosPerThread];
+    };
+    auto issue_loads = [&](float4 (&v0)[kMaxPosPerThread], float4 (&v1)[kMaxPosPerThread], uint32_t& meta) {
+      const int cbase = l_ks * 16 + sub * 8;
+      const float* src = nullptr;
+      int Csrc = 0, coff = 0;
+      if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
+      else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
+      meta = (src != nullptr) ? l_meta : 0u;
 #pragma unroll
-        for (int k = 0; k < kMaxPosPerThread; ++k) {
-          v0[k] = make_float4(0.f, 0.f, 0.f, 0.f); v1[k] = v0[k];
-          if (k < npos && src != nullptr && pix[k] >= 0) {
-            const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[k] * Csrc + coff);
-            v0[k] = __ldg(gp); v1[k] = __ldg(gp + 1);
-          }
+      for (int k = 0; k < kMaxPosPerThread; ++k) {
+        v0[k] = make_float4(0.f, 0.f, 0.f, 0.f); v1[k] = v0[k];
+        if ((meta >> (8 * k)) & 1u) {
+          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[k] * Csrc + coff);
+          v0[k] = __ldg(gp); v1[k] = __ldg(gp + 1);
         }
-        const int stage = (int)(g % (uint32_t)S);
-        const uint32_t ph = (g / (uint32_t)S) & 1u;
-        mbar_wait(empty + stage, ph ^ 1u);
-        uint8_t* dst = sA + (size_t)stage * L.slab_bytes + (size_t)sub * p.Palloc * 16;
+      }
+      if (++l_ks == kslabs) { l_ks = 0; ++l_it; if (l_it < my_tiles) decode_tile(l_it); }
+    };
+    auto process = [&](uint32_t g, const float4 (&v0)[kMaxPosPerThread], const float4 (&v1)[kMaxPosPerThread], uint32_t meta) {
+      const int it_ = (int)(g / (uint32_t)kslabs), ks = (int)(g % (uint32_t)kslabs);
+      const int cbase = ks * 16 + sub * 8;
+      const float* cA = coef + (size_t)(it_ & 1) * (2 * kMaxImgSlots * kMaxCin);
+      const float* cB = cA + kMaxImgSlots * kMaxCin;
+      if (p.pro != 0 && ks == 0) mbar_wait(cfull + (it_ & 1), ((uint32_t)it_ >> 1) & 1u);
+      const int stage = (int)(g % (uint32_t)S);
+      mbar_wait(empty + stage, ((g / (uint32_t)S) & 1u) ^ 1u);
+      uint8_t* dst = sA + (size_t)stage * L.slab_bytes + (size_t)sub * p.Palloc * 16;
 #pragma unroll
-        for (int k = 0; k < kMaxPosPerThread; ++k) {
-          const int pp = pos0 + k * 128;
-          if (k < npos && pp < p.P) {
-            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-            if (src != nullptr && pix[k] >= 0) {
-              float v[8] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
-              if (p.pro != 0) {
-                const float4* ca = reinterpret_cast<const float4*>(cA + slot[k] * kMaxCin + cbase);
-                const float4* cb = reinterpret_cast<const float4*>(cB + slot[k] * kMaxCin + cbase);
-                const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
-                v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
-                v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
-              }
-              if (p.act) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-              }
-              packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
-              packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+      for (int k = 0; k < kMaxPosPerThread; ++k) {
+        const int pp = pos0 + k * 128;
+        if (k < npos && pp < p.P) {
+          uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t m = meta >> (8 * k);
+          if (m & 1u) {
+            float v[8] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
+            if (p.pro != 0) {
+              const int slot = (int)((m >> 1) & 3u);
+              const float4* ca = reinterpret_cast<const float4*>(cA + slot * kMaxCin + cbase);
+              const float4* cb = reinterpret_cast<const float4*>(cB + slot * kMaxCin + cbase);
+              const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
+              v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
+              v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
             }
-            *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = packed;
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+            }
+            packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
+            packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
           }
+          *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = packed;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + stage);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(full + stage);
+        if (p.pro != 0 && ks == kslabs - 1) mbar_arrive(cempty + (it_ & 1));  // this warp is done with the table
+      }
+    };
+
+    if (total > 0) {
+      float4 a0[kMaxPosPerThread], a1[kMaxPosPerThread], b0[kMaxPosPerThread], b1[kMaxPosPerThread];
+      uint32_t ma = 0, mb = 0;
+      decode_tile(0);
+      issue_loads(a0, a1, ma);
+      for (uint32_t g = 0; g < total; g += 2) {
+        if (g + 1 < total) issue_loads(b0, b1, mb);
+        process(g, a0, a1, ma);
+        if (g + 1 < total) {
+          if (g + 2 < total) issue_loads(a0, a1, ma);
+          process(g + 1, b0, b1, mb);
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -292,6 +300,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
     }
     __syncwarp();
+  } else if (warp == kCoefWarp) {
+    // =========================================================================================== COEFFICIENTS
+    if (p.pro != 0) {
+      for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+        const int par = it & 1;
+        mbar_wait(cempty + par, (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int qh0 = tile * kTileM - halo;
+        const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+        float* cA = coef + (size_t)par * (2 * kMaxImgSlots * kMaxCin);
+        float* cB = cA + kMaxImgSlots * kMaxCin;
+        for (int i = lane; i < kMaxImgSlots * Ctot; i += 32) {
+          const int slot = i / Ctot, c = i - slot * Ctot;
+          const int n = n_first + slot;
+          float a = 0.f, b = 0.f;
+          if (n < p.B) {
+            const double* st;
+            int gs;
+            if (c < p.C0) { gs = p.gs0; st = p.st0 + ((size_t)n * (p.C0 / gs) + c / gs) * 2; }
+            else { gs = p.gs1; st = p.st1 + ((size_t)n * (p.C1 / gs) + (c - p.C0) / gs) * 2; }
+            const double cnt = (double)p.Hs * p.Ws * gs;
+            const double mean = st[0] / cnt;
+            double var = st[1] / cnt - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+            float sc, sh;
+            if (p.pro == 1) {
+              const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
+              sc = 1.f + __ldg(f + c);
+              sh = __ldg(f + Ctot + c);
+            } else {
+              sc = __ldg(p.gamma + c);
+              sh = __ldg(p.beta + c);
+            }
+            a = rstd * sc;
+            b = sh - (float)mean * a;
+          }
+          cA[slot * kMaxCin + c] = a;
+          cB[slot * kMaxCin + c] = b;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cfull + par);  // release: loaders acquire through the mbarrier
+      }
+    }
   } else {
     // =========================================================================================== EPILOGUE
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
