@@ -133,6 +133,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   const int Ctot = p.C0 + p.C1;
   const int S = p.stages;
   const int kslabs = p.Cin >> 4;
+  // contiguous tile range per CTA: neighbouring tiles share halo rows (L1/L2 hits) and, mostly, the image window, so
+  // the GN/FiLM coefficient table is rebuilt only when the window (n_first) changes ("epoch")
+  const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;  // balanced split
+  const int tile_begin = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
+  const int my_tiles = tiles_lo + ((int)blockIdx.x < tiles_rem ? 1 : 0);
+  auto first_image = [&](int tile) {
+    const int qh0 = tile * kTileM - halo;
+    return (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+  };
 
   // ---- setup
   if (tid == 0) {
@@ -162,7 +171,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     const int sub = tid & 1;
     const int pos0 = tid >> 1;
     const int npos = (p.P + 127) >> 7;  // passes needed (<= kMaxPosPerThread)
-    const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)kslabs;
 
     // load cursor state
@@ -170,9 +178,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     int pix[kMaxPosPerThread];
     uint32_t l_meta = 0;  // per position: bit (8k) valid, bits (8k+1..8k+2) image slot
     auto decode_tile = [&](int it_) {
-      const int q0 = ((int)blockIdx.x + it_ * (int)gridDim.x) * kTileM;
-      const int qh0 = q0 - halo;
-      const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+      const int qh0 = (tile_begin + it_) * kTileM - halo;
+      const int n_first = first_image(tile_begin + it_);
       l_meta = 0;
 #pragma unroll
       for (int k = 0; k < kMaxPosPerThread; ++k) {
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       int Csrc = 0, coff = 0;
       if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
       else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
-      meta = (src != nullptr) ? l_meta : 0u;
+      meta = (src != nullptr && !(p.dbg & 4)) ? l_meta : 0u;
 #pragma unroll
       for (int k = 0; k < kMaxPosPerThread; ++k) {
         v0[k] = make_float4(0.f, 0.f, 0.f, 0.f); v1[k] = v0[k];
@@ -209,12 +216,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
       if (++l_ks == kslabs) { l_ks = 0; ++l_it; if (l_it < my_tiles) decode_tile(l_it); }
     };
+    int p_epoch = -1, p_nfirst = -1;  // process-cursor view of the coefficient epoch
     auto process = [&](uint32_t g, const float4 (&v0)[kMaxPosPerThread], const float4 (&v1)[kMaxPosPerThread], uint32_t meta) {
       const int it_ = (int)(g / (uint32_t)kslabs), ks = (int)(g % (uint32_t)kslabs);
       const int cbase = ks * 16 + sub * 8;
-      const float* cA = coef + (size_t)(it_ & 1) * (2 * kMaxImgSlots * kMaxCin);
+      if (p.pro != 0 && ks == 0) {
+        const int nf = first_image(tile_begin + it_);
+        if (nf != p_nfirst) {
+          if (p_epoch >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(cempty + (p_epoch & 1)); }  // done with old table
+          ++p_epoch; p_nfirst = nf;
+          mbar_wait(cfull + (p_epoch & 1), ((uint32_t)p_epoch >> 1) & 1u);
+        }
+      }
+      const float* cA = coef + (size_t)(p_epoch & 1) * (2 * kMaxImgSlots * kMaxCin);
       const float* cB = cA + kMaxImgSlots * kMaxCin;
-      if (p.pro != 0 && ks == 0) mbar_wait(cfull + (it_ & 1), ((uint32_t)it_ >> 1) & 1u);
       const int stage = (int)(g % (uint32_t)S);
       mbar_wait(empty + stage, ((g / (uint32_t)S) & 1u) ^ 1u);
       uint8_t* dst = sA + (size_t)stage * L.slab_bytes + (size_t)sub * p.Palloc * 16;
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
               v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
               v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
             }
-            if (p.act) {
+            if (p.act && !(p.dbg & 16)) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
             }
@@ -246,10 +261,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(full + stage);
-        if (p.pro != 0 && ks == kslabs - 1) mbar_arrive(cempty + (it_ & 1));  // this warp is done with the table
-      }
+      if (lane == 0) mbar_arrive(full + stage);
     };
 
     if (total > 0) {
@@ -268,31 +280,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     }
   } else if (warp == kMmaWarp) {
     // =========================================================================================== MMA ISSUER
-    if (lane == 0) {
+    // One thread.  Descriptor words are precomputed: per MMA only the 14-bit start-address fields change
+    // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
+    if (lane == 0 && my_tiles > 0) {
       mbar_wait(wbar, 0);
       const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
-      const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
       const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
-      const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
+      const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t slab16 = L.slab_bytes >> 4;
+      const uint32_t tap16 = ((uint32_t)p.Cin * p.CoutPad * 2) >> 4;     // bytes of one tap of weights, /16
+      const uint32_t kstep16 = (2u * b_lbo) >> 4;                          // one 16-channel slab of weights, /16
+      uint32_t shift[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) shift[t] = (uint32_t)(halo + ((p.taps == 9) ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
       uint32_t g = 0;
-      for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+      for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         mbar_wait(tempty + b, (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
-        uint32_t acc = 0;
         for (int ks = 0; ks < kslabs; ++ks, ++g) {
-          const int stage = (int)(g % (uint32_t)S);
+          const uint32_t stage = g % (uint32_t)S;
           mbar_wait(full + stage, (g / (uint32_t)S) & 1u);
           tc_fence_after_sync();
-          const uint32_t slab = a_base + (uint32_t)stage * L.slab_bytes;
-          for (int t = 0; t < p.taps; ++t) {
-            int shift = halo;
-            if (p.taps == 9) shift += (t / 3 - 1) * p.PW + (t % 3 - 1);
-            const uint64_t ad = umma_desc(slab + (uint32_t)shift * 16, a_lbo, 128);
-            const uint64_t bd = umma_desc(w_base + (uint32_t)t * tap_bytes + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-            umma_f16(d_tmem, ad, bd, idesc, acc);
-            acc = 1;
+          const uint32_t a_lo = a_lo0 + stage * slab16;
+          const uint32_t b_lo = b_lo0 + (uint32_t)ks * kstep16;
+          if (!(p.dbg & 2)) {
+            if (p.taps == 9) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)t * tap16);
+                umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
+              }
+            } else {
+              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[0]);
+              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)b_lo;
+              umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty + stage);  // slab reusable once these MMAs retire
         }
@@ -303,17 +330,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   } else if (warp == kCoefWarp) {
     // =========================================================================================== COEFFICIENTS
     if (p.pro != 0) {
-      for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
-        const int par = it & 1;
-        mbar_wait(cempty + par, (((uint32_t)it >> 1) & 1u) ^ 1u);
-        const int qh0 = tile * kTileM - halo;
-        const int n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+      int epoch = -1, nfirst = -1;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int nf = first_image(tile_begin + it);
+        if (nf == nfirst) continue;
+        nfirst = nf; ++epoch;
+        const int par = epoch & 1;
+        mbar_wait(cempty + par, (((uint32_t)epoch >> 1) & 1u) ^ 1u);
         float* cA = coef + (size_t)par * (2 * kMaxImgSlots * kMaxCin);
         float* cB = cA + kMaxImgSlots * kMaxCin;
         for (int i = lane; i < kMaxImgSlots * Ctot; i += 32) {
           const int slot = i / Ctot, c = i - slot * Ctot;
-          const int n = n_first + slot;
-          float a = 0.f, b = 0.f;
+          const int n = nf + slot;
+          float a = 0.f, bb = 0.f;
           if (n < p.B) {
             const double* st;
             int gs;
@@ -334,10 +363,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
               sh = __ldg(p.beta + c);
             }
             a = rstd * sc;
-            b = sh - (float)mean * a;
+            bb = sh - (float)mean * a;
           }
           cA[slot * kMaxCin + c] = a;
-          cB[slot * kMaxCin + c] = b;
+          cB[slot * kMaxCin + c] = bb;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(cfull + par);  // release: loaders acquire through the mbarrier
@@ -349,9 +378,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     const int nchunks = p.CoutPad >> 4;
     const bool vec_ok = (p.Cout & 3) == 0;
     const int G = p.ostats ? p.Cout / p.ogs : 1;
-    for (int it = 0, tile = blockIdx.x; tile < p.num_tiles; ++it, tile += gridDim.x) {
+    for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
-      const int q = tile * kTileM + quarter * 32 + lane;
+      const int q = (tile_begin + it) * kTileM + quarter * 32 + lane;
       bool valid = false;
       int n = p.B;  // out-of-range rows belong to no image
       size_t opix = 0;
@@ -368,6 +397,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         }
         opix = ((size_t)n * Ho + yo) * Wo + xo;
       }
+      if (p.dbg & 8) valid = false;
       const int n_lo = __shfl_sync(0xffffffffu, n, 0), n_hi = __shfl_sync(0xffffffffu, n, 31);
       float* orow = p.out + opix * p.Cout;
       const float* rrow = p.resid ? p.resid + opix * p.Cout : nullptr;
