@@ -17,7 +17,7 @@ class ConvDesc(C.Structure):
         ("stats0", _vp), ("stats1", _vp), ("gs0", _i), ("gs1", _i),
         ("film", _vp), ("film_stride", _i), ("film_off", _i), ("gamma", _vp), ("beta", _vp), ("eps", _f),
         ("wpk", _vp), ("bias", _vp), ("Cout", _i), ("CoutPad", _i),
-        ("residual", _vp), ("out", _vp), ("out_stats", _vp), ("out_gs", _i), ("debug", _i),
+        ("residual", _vp), ("out", _vp), ("out_stats", _vp), ("out_gs", _i), ("debug", _i), ("debug_buf", _vp),
     ]
 
 

@@ -87,15 +87,24 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   p->wpk = reinterpret_cast<const __half*>(d->wpk); p->bias = d->bias; p->Cout = d->Cout; p->CoutPad = d->CoutPad;
   p->resid = d->residual; p->out = d->out; p->ostats = d->out_stats; p->ogs = d->out_gs > 0 ? d->out_gs : d->Cout;
   if (d->out_stats) DMD_CHECK(d->out_gs > 0 && d->Cout % d->out_gs == 0 && d->out_gs % 16 == 0, "conv: out_gs=%d must divide Cout and be a multiple of 16", d->out_gs);
-  p->dbg = d->debug;
+  p->dbg = d->debug; p->dbg_buf = (long long*)d->debug_buf;
   p->PW = p->W + 1; p->PH = p->H + 1;
   const long long Q = (long long)p->B * p->PH * p->PW;
   DMD_CHECK(Q * (p->PW > p->PH ? p->PW : p->PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
   p->Q = (int)Q;
   const int halo = d->taps == 9 ? p->PW + 1 : 0;
   p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
-  DMD_CHECK(p->P <= 128 * kMaxPosPerThread, "conv: W=%d too wide for the linear halo (P=%d > %d); needs the strip path", p->W, p->P, 128 * kMaxPosPerThread);
+  p->group_warps = ((2 * p->P + kItemsPerThread - 1) / kItemsPerThread + 31) / 32;
+  if (p->group_warps < 2) p->group_warps = 2;
+  DMD_CHECK(p->group_warps <= kMaxGroupWarps, "conv: W=%d too wide for the linear halo (P=%d); needs the strip path", p->W, p->P);
   DMD_CHECK((p->P + p->PH * p->PW - 1) / (p->PH * p->PW) + 1 <= kMaxImgSlots, "conv: image too small for tile (H=%d W=%d)", p->H, p->W);
+  if (d->out_stats) DMD_CHECK(p->PH * p->PW >= 64, "conv: image too small for the statistics epilogue (a tile may touch at most %d images)", kStatSlots);
+  if (d->out_stats) {
+    const int L4 = d->Cout / 4;
+    DMD_CHECK(d->Cout % 4 == 0 && (L4 == 4 || L4 == 8 || L4 == 16 || L4 == 32), "conv: out_stats needs Cout in {16,32,64,128} (got %d)", d->Cout);
+    DMD_CHECK(d->out_gs == 16 || d->out_gs == 32 || d->out_gs == 64 || d->out_gs == 128, "conv: out_gs must be 16/32/64/128");
+    DMD_CHECK(d->Cout / d->out_gs <= kMaxOutGroups, "conv: too many output groups");
+  }
   p->dPW.init(p->PW); p->dPH.init(p->PH);
   p->num_tiles = (p->Q + kTileM - 1) / kTileM;
   // slab ring depth: as many 16-channel slabs as fit next to the resident weights, at most two tiles' worth
@@ -103,7 +112,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   const ConvSmemLayout L0 = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, 0);
   const long long budget = 227ll * 1024 - (long long)L0.total;
   int stages = (int)(budget / (long long)L0.slab_bytes);
-  if (stages > 2 * kslabs) stages = 2 * kslabs;
+  if (stages > 2 * kslabs && stages > 6) stages = 2 * kslabs > 6 ? 2 * kslabs : 6;
   if (stages > kMaxStages) stages = kMaxStages;
   DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
   p->stages = stages;
@@ -134,7 +143,8 @@ template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
-  conv_tc_kernel<kCols><<<grid, kConvThreads, smem, st>>>(p);
+  const int threads = (kLoadGroups * p.group_warps + 1 + kEpiWarps) * 32;
+  conv_tc_kernel<kCols><<<grid, threads, smem, st>>>(p);
   DMD_LAUNCH_OK();
   return 0;
 }

@@ -15,13 +15,16 @@
 //     slab = [2 chunks of 8 channels][P positions][16 B]          (LBO = Palloc*16, SBO = 128)
 // and every tap reads the same slab through a descriptor whose start address is shifted by (dy*PW+dx)*16 B.
 //
-// Roles (416 threads, one CTA per SM, tiles strided over the grid):
-//   warps 0-7   loaders : global fp32 -> GN/FiLM affine -> SiLU -> fp16 -> slab ring (full/empty mbarriers)
-//   warp  8     MMA     : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap); tcgen05.commit frees
-//                         the slab and, after the last slab, publishes the TMEM accumulator
-//   warps 9-12  epilogue: tcgen05.ld accumulator rows, + bias + residual, store NHWC, GroupNorm partial sums
-//   warp  13    coef    : per-(image, channel) prologue coefficients a = rstd*(1+scale), b = shift - mean*a for the tile
-//                         AFTER the one being loaded (fp64 statistics -> fp32), double-buffered in shared memory
+// Roles (one CTA per SM, each CTA owns a contiguous range of tiles):
+//   3 loader groups (WG warps each): group j produces slabs g = j, j+3, ... of the CTA's slab sequence, so three slabs are
+//       in flight and global-load latency is hidden ACROSS groups.  (It cannot be hidden inside a thread: the
+//       generic->async proxy fence a writer must execute before the MMA may read its slab is a MEMBAR that also drains
+//       that thread's outstanding loads.)  Per slab a thread issues the loads of its 3 (position, 8-channel) items,
+//       computes the slab's GroupNorm/FiLM coefficients while they fly, applies affine + SiLU, converts to fp16, stores.
+//   1 MMA warp  : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap) from precomputed descriptor
+//       words; tcgen05.commit frees the slab and, after the last slab of a tile, publishes the TMEM accumulator.
+//   8 epilogue warps: TMEM -> registers (+bias) -> shared staging (transpose) -> coalesced 16-byte global stores with the
+//       residual added on the way and GroupNorm (sum, sumsq) partials reduced per tile.
 // Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
 // TMEM holds two accumulators so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #pragma once
@@ -29,17 +32,18 @@
 
 namespace dmd {
 
-constexpr int kLoadWarps = 8;
-constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kMmaWarp = kLoadWarps;           // warp 8
-constexpr int kEpiWarp0 = kLoadWarps + 1;      // warps 9..12
-constexpr int kCoefWarp = kLoadWarps + 5;       // warp 13: GN/FiLM coefficients, one tile ahead of the loaders
-constexpr int kConvThreads = (kLoadWarps + 6) * 32;  // 448
+constexpr int kLoadGroups = 3;
+constexpr int kItemsPerThread = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMaxGroupWarps = 6;
+constexpr int kMaxConvThreads = (kLoadGroups * kMaxGroupWarps + 1 + kEpiWarps) * 32;  // 864
 constexpr int kTileM = 128;
 constexpr int kMaxImgSlots = 4;
 constexpr int kMaxCin = 128;
 constexpr int kMaxStages = 16;
-constexpr int kMaxPosPerThread = 4;  // ceil(P / 128) with P <= 512
+constexpr int kStatSlots = 3;   // images a 128-row tile can touch
+constexpr int kMaxOutGroups = 4;
 
 struct FastDiv {
   uint32_t d, m;
@@ -86,20 +90,26 @@ struct ConvParams {
   int PW, PH, Q;      // pitch, rows per image, total positions B*PH*PW
   int P, Palloc;      // halo positions, odd allocation pitch
   int num_tiles, stages;
+  int group_warps;    // WG: warps per loader group (ceil(2P / 3 / 32))
   FastDiv dPW, dPH;
   int dbg;
+  long long* dbg_buf;  // bring-up: clock64 timeline of CTA 0, [role 3][tile 16][event 16]
 };
 
 struct ConvSmemLayout {
-  uint32_t coef_off, w_off, a_off, slab_bytes, total;
+  uint32_t ctab_off, bias_off, rowinfo_off, sstat_off, stage_off, w_off, a_off, slab_bytes, stage_pitch, total;
 };
 
-// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], cfull[2], cempty[2], tmem slot
+// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], tmem slot
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
-  L.coef_off = 512;
-  const uint32_t coef_bytes = 2u * kMaxImgSlots * kMaxCin * 2 * sizeof(float);  // two parities x (a, b)
-  L.w_off = (L.coef_off + coef_bytes + 127u) & ~127u;
+  L.ctab_off = 512;  // [group 3][parity 2][a|b][slot 4][16 ch] floats
+  L.bias_off = L.ctab_off + kLoadGroups * 2 * 2 * kMaxImgSlots * 16 * 4;
+  L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
+  L.sstat_off = L.rowinfo_off + kTileM * 8;          // [slot 3][group 4][2] floats
+  L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
+  L.stage_off = (L.sstat_off + kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
+  L.w_off = (L.stage_off + kTileM * L.stage_pitch + 127u) & ~127u;
   const uint32_t w_bytes = (uint32_t)taps * Cin * CoutPad * 2;
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
   L.slab_bytes = 2u * Palloc * 16;
@@ -111,239 +121,123 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+#define DMD_TS(role, it_, ev) \
+  do { if (p.dbg_buf && blockIdx.x == 0 && (it_) < 16) p.dbg_buf[((role) * 16 + (it_)) * 16 + (ev)] = clock64(); } while (0)
+
 template <int kAccCols>  // TMEM columns per accumulator (>= CoutPad); two accumulators are allocated
-__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* full = wbar + 1;                 // [kMaxStages]
   uint64_t* empty = full + kMaxStages;       // [kMaxStages]
   uint64_t* tfull = empty + kMaxStages;      // [2]
   uint64_t* tempty = tfull + 2;              // [2]
-  uint64_t* cfull = tempty + 2;              // [2] coefficient table ready
-  uint64_t* cempty = cfull + 2;              // [2] coefficient table consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc, p.stages);
-  float* coef = reinterpret_cast<float*>(smem + L.coef_off);  // [parity][a|b][slot][kMaxCin]
+  float* ctab = reinterpret_cast<float*>(smem + L.ctab_off);
+  float* sbias = reinterpret_cast<float*>(smem + L.bias_off);
+  int2* rowinfo = reinterpret_cast<int2*>(smem + L.rowinfo_off);
+  float* sstat = reinterpret_cast<float*>(smem + L.sstat_off);
+  uint8_t* sStage = smem + L.stage_off;
   uint8_t* sW = smem + L.w_off;
   uint8_t* sA = smem + L.a_off;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int WG = p.group_warps;
+  const int GT = WG * 32;
+  const int mma_warp = kLoadGroups * WG;
+  const int epi_warp0 = mma_warp + 1;
   const int halo = (p.taps == 9) ? (p.PW + 1) : 0;
   const int Ctot = p.C0 + p.C1;
   const int S = p.stages;
   const int kslabs = p.Cin >> 4;
-  // contiguous tile range per CTA: neighbouring tiles share halo rows (L1/L2 hits) and, mostly, the image window, so
-  // the GN/FiLM coefficient table is rebuilt only when the window (n_first) changes ("epoch")
-  const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;  // balanced split
+  // contiguous, balanced tile range per CTA: neighbouring tiles share halo rows (L1/L2 hits)
+  const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
   const int my_tiles = tiles_lo + ((int)blockIdx.x < tiles_rem ? 1 : 0);
-  auto first_image = [&](int tile) {
-    const int qh0 = tile * kTileM - halo;
-    return (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
-  };
 
   // ---- setup
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, kLoadWarps); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull + b, 1); mbar_init(tempty + b, 4);
-      mbar_init(cfull + b, 1); mbar_init(cempty + b, kLoadWarps);
-    }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, WG); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     mbar_expect_tx(wbar, tap_bytes * p.taps);
     for (int t = 0; t < p.taps; ++t)
       bulk_g2s(sW + (size_t)t * tap_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)t * tap_bytes, tap_bytes, wbar);
   }
-  if (warp == kMmaWarp) tmem_alloc<2 * kAccCols>(tmem_slot);
+  if (warp == mma_warp) tmem_alloc<2 * kAccCols>(tmem_slot);
+  for (int i = tid; i < 128; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  for (int i = tid; i < kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kLoadWarps) {
-    // =========================================================================================== LOADERS
-    // Software pipeline: the global loads of slab g+1 (possibly the first slab of the NEXT tile) are in flight while
-    // slab g is normalised and written to the ring.  Every thread owns halo positions pos0, pos0+128, ... and one of
-    // the two 8-channel chunks of each slab; per-tile pixel offsets are decoded once.
-    const int sub = tid & 1;
-    const int pos0 = tid >> 1;
-    const int npos = (p.P + 127) >> 7;  // passes needed (<= kMaxPosPerThread)
-    const uint32_t total = (uint32_t)my_tiles * (uint32_t)kslabs;
-
-    // load cursor state
-    int l_it = 0, l_ks = 0;
-    int pix[kMaxPosPerThread];
-    uint32_t l_meta = 0;  // per position: bit (8k) valid, bits (8k+1..8k+2) image slot
-    auto decode_tile = [&](int it_) {
-      const int qh0 = (tile_begin + it_) * kTileM - halo;
-      const int n_first = first_image(tile_begin + it_);
-      l_meta = 0;
+  if (warp < mma_warp) {
+    // =========================================================================================== LOADER GROUPS
+    const int grp = warp / WG;
+    const int gt = tid - grp * GT;  // thread index inside the group
+    const int total = my_tiles * kslabs;
+    float* my_ctab = ctab + (size_t)grp * (2 * 2 * kMaxImgSlots * 16);
+    int cur_it = -1, n_first = 0;
+    int pix[kItemsPerThread];
+    uint32_t meta = 0;       // per item: bit (8j) = valid pixel, bits (8j+1..8j+2) = image slot
+    uint32_t tab_parity = 0; // this group's coefficient table is double-buffered per slab
+    int stage = grp % S;     // ring position of this group's first slab
+    uint32_t phase = (uint32_t)(grp / S) & 1u;
+    int it = 0, ks = grp;
+    while (ks >= kslabs) { ks -= kslabs; ++it; }
+    for (int g = grp; g < total; g += kLoadGroups) {
+      if (it != cur_it) {  // decode this thread's items for the new tile
+        cur_it = it;
+        const int qh0 = (tile_begin + it) * kTileM - halo;
+        n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
+        meta = 0;
 #pragma unroll
-      for (int k = 0; k < kMaxPosPerThread; ++k) {
-        pix[k] = -1;
-        const int pp = pos0 + k * 128;
-        const int q = qh0 + pp;
-        if (k < npos && pp < p.P && q >= 0 && q < p.Q) {
-          const uint32_t R = p.dPW.div((uint32_t)q);
-          const int x = q - (int)R * p.PW;
-          const uint32_t n = p.dPH.div(R);
-          const int y = (int)R - (int)n * p.PH;
-          if (x < p.W && y < p.H) {
-            const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-            pix[k] = ((int)n * p.Hs + ys) * p.Ws + xs;
-            l_meta |= (1u | ((uint32_t)((int)n - n_first) << 1)) << (8 * k);
-          }
-        }
-      }
-    };
-    auto issue_loads = [&](float4 (&v0)[kMaxPosPerThread], float4 (&v1)[kMaxPosPerThread], uint32_t& meta) {
-      const int cbase = l_ks * 16 + sub * 8;
-      const float* src = nullptr;
-      int Csrc = 0, coff = 0;
-      if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
-      else if (cbase < Ctot) { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
-      meta = (src != nullptr && !(p.dbg & 4)) ? l_meta : 0u;
-#pragma unroll
-      for (int k = 0; k < kMaxPosPerThread; ++k) {
-        v0[k] = make_float4(0.f, 0.f, 0.f, 0.f); v1[k] = v0[k];
-        if ((meta >> (8 * k)) & 1u) {
-          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[k] * Csrc + coff);
-          v0[k] = __ldg(gp); v1[k] = __ldg(gp + 1);
-        }
-      }
-      if (++l_ks == kslabs) { l_ks = 0; ++l_it; if (l_it < my_tiles) decode_tile(l_it); }
-    };
-    int p_epoch = -1, p_nfirst = -1;  // process-cursor view of the coefficient epoch
-    auto process = [&](uint32_t g, const float4 (&v0)[kMaxPosPerThread], const float4 (&v1)[kMaxPosPerThread], uint32_t meta) {
-      const int it_ = (int)(g / (uint32_t)kslabs), ks = (int)(g % (uint32_t)kslabs);
-      const int cbase = ks * 16 + sub * 8;
-      if (p.pro != 0 && ks == 0) {
-        const int nf = first_image(tile_begin + it_);
-        if (nf != p_nfirst) {
-          if (p_epoch >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(cempty + (p_epoch & 1)); }  // done with old table
-          ++p_epoch; p_nfirst = nf;
-          mbar_wait(cfull + (p_epoch & 1), ((uint32_t)p_epoch >> 1) & 1u);
-        }
-      }
-      const float* cA = coef + (size_t)(p_epoch & 1) * (2 * kMaxImgSlots * kMaxCin);
-      const float* cB = cA + kMaxImgSlots * kMaxCin;
-      const int stage = (int)(g % (uint32_t)S);
-      mbar_wait(empty + stage, ((g / (uint32_t)S) & 1u) ^ 1u);
-      uint8_t* dst = sA + (size_t)stage * L.slab_bytes + (size_t)sub * p.Palloc * 16;
-#pragma unroll
-      for (int k = 0; k < kMaxPosPerThread; ++k) {
-        const int pp = pos0 + k * 128;
-        if (k < npos && pp < p.P) {
-          uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-          const uint32_t m = meta >> (8 * k);
-          if (m & 1u) {
-            float v[8] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
-            if (p.pro != 0) {
-              const int slot = (int)((m >> 1) & 3u);
-              const float4* ca = reinterpret_cast<const float4*>(cA + slot * kMaxCin + cbase);
-              const float4* cb = reinterpret_cast<const float4*>(cB + slot * kMaxCin + cbase);
-              const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
-              v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
-              v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
-            }
-            if (p.act && !(p.dbg & 16)) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-            }
-            packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
-            packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
-          }
-          *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = packed;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full + stage);
-    };
-
-    if (total > 0) {
-      float4 a0[kMaxPosPerThread], a1[kMaxPosPerThread], b0[kMaxPosPerThread], b1[kMaxPosPerThread];
-      uint32_t ma = 0, mb = 0;
-      decode_tile(0);
-      issue_loads(a0, a1, ma);
-      for (uint32_t g = 0; g < total; g += 2) {
-        if (g + 1 < total) issue_loads(b0, b1, mb);
-        process(g, a0, a1, ma);
-        if (g + 1 < total) {
-          if (g + 2 < total) issue_loads(a0, a1, ma);
-          process(g + 1, b0, b1, mb);
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // =========================================================================================== MMA ISSUER
-    // One thread.  Descriptor words are precomputed: per MMA only the 14-bit start-address fields change
-    // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
-    if (lane == 0 && my_tiles > 0) {
-      mbar_wait(wbar, 0);
-      const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
-      const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
-      const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
-      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
-      const uint32_t b_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
-      const uint32_t slab16 = L.slab_bytes >> 4;
-      const uint32_t tap16 = ((uint32_t)p.Cin * p.CoutPad * 2) >> 4;     // bytes of one tap of weights, /16
-      const uint32_t kstep16 = (2u * b_lbo) >> 4;                          // one 16-channel slab of weights, /16
-      uint32_t shift[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) shift[t] = (uint32_t)(halo + ((p.taps == 9) ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
-      uint32_t g = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int b = it & 1;
-        mbar_wait(tempty + b, (((uint32_t)it >> 1) & 1u) ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
-        for (int ks = 0; ks < kslabs; ++ks, ++g) {
-          const uint32_t stage = g % (uint32_t)S;
-          mbar_wait(full + stage, (g / (uint32_t)S) & 1u);
-          tc_fence_after_sync();
-          const uint32_t a_lo = a_lo0 + stage * slab16;
-          const uint32_t b_lo = b_lo0 + (uint32_t)ks * kstep16;
-          if (!(p.dbg & 2)) {
-            if (p.taps == 9) {
-#pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
-                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)t * tap16);
-                umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
-              }
-            } else {
-              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[0]);
-              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)b_lo;
-              umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
+        for (int j = 0; j < kItemsPerThread; ++j) {
+          pix[j] = 0;
+          const int pp = (gt + j * GT) >> 1;
+          const int q = qh0 + pp;
+          if (pp < p.P && q >= 0 && q < p.Q) {
+            const uint32_t R = p.dPW.div((uint32_t)q);
+            const int x = q - (int)R * p.PW;
+            const uint32_t n = p.dPH.div(R);
+            const int y = (int)R - (int)n * p.PH;
+            if (x < p.W && y < p.H) {
+              const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
+              pix[j] = ((int)n * p.Hs + ys) * p.Ws + xs;
+              meta |= (1u | ((uint32_t)((int)n - n_first) << 1)) << (8 * j);
             }
           }
-          umma_commit(empty + stage);  // slab reusable once these MMAs retire
         }
-        umma_commit(tfull + b);        // accumulator complete
       }
-    }
-    __syncwarp();
-  } else if (warp == kCoefWarp) {
-    // =========================================================================================== COEFFICIENTS
-    if (p.pro != 0) {
-      int epoch = -1, nfirst = -1;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int nf = first_image(tile_begin + it);
-        if (nf == nfirst) continue;
-        nfirst = nf; ++epoch;
-        const int par = epoch & 1;
-        mbar_wait(cempty + par, (((uint32_t)epoch >> 1) & 1u) ^ 1u);
-        float* cA = coef + (size_t)par * (2 * kMaxImgSlots * kMaxCin);
-        float* cB = cA + kMaxImgSlots * kMaxCin;
-        for (int i = lane; i < kMaxImgSlots * Ctot; i += 32) {
-          const int slot = i / Ctot, c = i - slot * Ctot;
-          const int n = nf + slot;
+      // ---- issue all loads of this slab
+      float4 v0[kItemsPerThread], v1[kItemsPerThread];
+#pragma unroll
+      for (int j = 0; j < kItemsPerThread; ++j) {
+        const int sub = (gt + j * GT) & 1;
+        const int cbase = ks * 16 + sub * 8;
+        v0[j] = make_float4(0.f, 0.f, 0.f, 0.f); v1[j] = v0[j];
+        if (((meta >> (8 * j)) & 1u) && cbase < Ctot && !(p.dbg & 4)) {
+          const float* src; int Csrc, coff;
+          if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
+          else { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
+          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[j] * Csrc + coff);
+          v0[j] = __ldg(gp); v1[j] = __ldg(gp + 1);
+        }
+      }
+      // ---- coefficients of this slab's 16 channels for the (<= 4) images the tile touches, while the loads fly
+      float* tA = my_ctab + (size_t)tab_parity * (2 * kMaxImgSlots * 16);
+      float* tB = tA + kMaxImgSlots * 16;
+      if (p.pro != 0) {
+        if (gt < kMaxImgSlots * 16) {
+          const int slot = gt >> 4, c = ks * 16 + (gt & 15);
+          const int n = n_first + slot;
           float a = 0.f, bb = 0.f;
-          if (n < p.B) {
+          if (n < p.B && c < Ctot) {
             const double* st;
             int gs;
             if (c < p.C0) { gs = p.gs0; st = p.st0 + ((size_t)n * (p.C0 / gs) + c / gs) * 2; }
@@ -365,119 +259,258 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             a = rstd * sc;
             bb = sh - (float)mean * a;
           }
-          cA[slot * kMaxCin + c] = a;
-          cB[slot * kMaxCin + c] = bb;
+          tA[gt] = a;   // [slot][16]
+          tB[gt] = bb;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cfull + par);  // release: loaders acquire through the mbarrier
+        named_bar_sync(1 + grp, GT);
       }
-    }
-  } else {
-    // =========================================================================================== EPILOGUE
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int nchunks = p.CoutPad >> 4;
-    const bool vec_ok = (p.Cout & 3) == 0;
-    const int G = p.ostats ? p.Cout / p.ogs : 1;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = it & 1;
-      const int q = (tile_begin + it) * kTileM + quarter * 32 + lane;
-      bool valid = false;
-      int n = p.B;  // out-of-range rows belong to no image
-      size_t opix = 0;
-      if (q < p.Q) {
-        const uint32_t R = p.dPW.div((uint32_t)q);
-        const int x = q - (int)R * p.PW;
-        n = (int)p.dPH.div(R);
-        const int y = (int)R - n * p.PH;
-        valid = (x < p.W) && (y < p.H);
-        int yo = y, xo = x, Ho = p.H, Wo = p.W;
-        if (p.stride == 2) {
-          valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
-          yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
-        }
-        opix = ((size_t)n * Ho + yo) * Wo + xo;
-      }
-      if (p.dbg & 8) valid = false;
-      const int n_lo = __shfl_sync(0xffffffffu, n, 0), n_hi = __shfl_sync(0xffffffffu, n, 31);
-      float* orow = p.out + opix * p.Cout;
-      const float* rrow = p.resid ? p.resid + opix * p.Cout : nullptr;
-      // prefetch the residual of the first chunk while the MMAs are still running
-      float4 rnext[4];
+      // ---- wait for the ring slot, transform, store
+      if (gt == 0) DMD_TS(0, it, ks * 3 + 0);
+      mbar_wait(empty + stage, phase ^ 1u);
+      if (gt == 0) DMD_TS(0, it, ks * 3 + 1);
+      uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && rrow && vec_ok && 16 <= p.Cout) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow) + i);
-      }
-      mbar_wait(tfull + b, ((uint32_t)it >> 1) & 1u);
-      tc_fence_after_sync();
-      const uint32_t trow = tmem_base + (uint32_t)b * kAccCols + ((uint32_t)(quarter * 32) << 16);
-      float s = 0.f, ss = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)ch * 16, v);
-        const int c0 = ch * 16;
-        float4 rcur[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { rcur[i] = rnext[i]; rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
-        if (valid && rrow && vec_ok && c0 + 32 <= p.Cout) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 16) + i);
-        }
-        if (valid) {
-          if (vec_ok && c0 + 16 <= p.Cout) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0) + i) : make_float4(0, 0, 0, 0);
-              v[4 * i + 0] += bv.x + rcur[i].x; v[4 * i + 1] += bv.y + rcur[i].y;
-              v[4 * i + 2] += bv.z + rcur[i].z; v[4 * i + 3] += bv.w + rcur[i].w;
-              *reinterpret_cast<float4*>(orow + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int j = 0; j < kItemsPerThread; ++j) {
+        const int item = gt + j * GT;
+        const int pp = item >> 1, sub = item & 1;
+        if (pp < p.P) {
+          uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t m = meta >> (8 * j);
+          if ((m & 1u) && (ks * 16 + sub * 8) < Ctot) {
+            float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
+            if (p.pro != 0) {
+              const int slot = (int)((m >> 1) & 3u);
+              const float4* ca = reinterpret_cast<const float4*>(tA + slot * 16 + sub * 8);
+              const float4* cb = reinterpret_cast<const float4*>(tB + slot * 16 + sub * 8);
+              const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
+              v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
+              v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
             }
-          } else {
+            if (p.act && !(p.dbg & 16)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (c0 + i < p.Cout) {
-                v[i] += (p.bias ? __ldg(p.bias + c0 + i) : 0.f) + (rrow ? __ldg(rrow + c0 + i) : 0.f);
-                orow[c0 + i] = v[i];
-              } else {
-                v[i] = 0.f;
+              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+            }
+            packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
+            packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+          }
+          *reinterpret_cast<uint4*>(slab + (size_t)sub * p.Palloc * 16 + (size_t)pp * 16) = packed;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + stage);
+      if (gt == 0) DMD_TS(0, it, ks * 3 + 2);
+      // advance by kLoadGroups slabs
+      tab_parity ^= 1u;
+      ks += kLoadGroups;
+      while (ks >= kslabs) { ks -= kslabs; ++it; }
+      stage += kLoadGroups;
+      while (stage >= S) { stage -= S; phase ^= 1u; }
+    }
+  } else if (warp == mma_warp) {
+    // =========================================================================================== MMA ISSUER
+    // One thread.  Descriptor words are precomputed: per MMA only the 14-bit start-address fields change
+    // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
+      const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
+      const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t slab16 = L.slab_bytes >> 4;
+      const uint32_t tap16 = ((uint32_t)p.Cin * p.CoutPad * 2) >> 4;     // bytes of one tap of weights, /16
+      const uint32_t kstep16 = (2u * b_lbo) >> 4;                          // one 16-channel slab of weights, /16
+      uint32_t shift[9], b_tap[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        shift[t] = (uint32_t)(halo + ((p.taps == 9) ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
+        b_tap[t] = (uint32_t)t * tap16;
+      }
+      uint32_t stage = 0, phase = 0, a_lo = a_lo0;
+      uint32_t tph0 = 1u, tph1 = 1u;  // parity to wait on for tempty[b]: first use passes immediately
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        DMD_TS(1, it, 12);
+        mbar_wait(tempty + b, b ? tph1 : tph0);
+        DMD_TS(1, it, 13);
+        if (b) tph1 ^= 1u; else tph0 ^= 1u;
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
+        uint32_t b_lo = b_lo0;
+        for (int ks = 0; ks < kslabs; ++ks) {
+          DMD_TS(1, it, ks * 3 + 0);
+          mbar_wait(full + stage, phase);
+          DMD_TS(1, it, ks * 3 + 1);
+          tc_fence_after_sync();
+          if (!(p.dbg & 2)) {
+            if (p.taps == 9) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + b_tap[t]);
+                umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
               }
+            } else {
+              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[0]);
+              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)b_lo;
+              umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { s += v[i]; ss += v[i] * v[i]; }
+          umma_commit(empty + stage);  // slab reusable once these MMAs retire
+          DMD_TS(1, it, ks * 3 + 2);
+          b_lo += kstep16;
+          a_lo += slab16;
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
         }
-        if (p.ostats != nullptr) {  // flush GroupNorm partials at a group boundary
-          const int cnext = c0 + 16;
-          if ((cnext % p.ogs) == 0 || cnext >= p.Cout) {
-            const int grp = c0 / p.ogs;
-            if (grp < G) {
-              for (int img = n_lo; img <= n_hi; ++img) {
-                if (img >= p.B) continue;
-                float a = (valid && n == img) ? s : 0.f, bq = (valid && n == img) ? ss : 0.f;
+        umma_commit(tfull + b);        // accumulator complete
+        DMD_TS(1, it, 14);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================================== EPILOGUE (8 warps)
+    const int et = tid - epi_warp0 * 32;       // 0..255
+    const int ew = et >> 5;                    // 0..7
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int first_of_quarter = (ew < 4) ? 1 : 0;   // epilogue warps ew and ew+4 share (warp & 3): they split the columns
+    const int nchunks = p.CoutPad >> 4;
+    const int ch_half = (nchunks + 1) >> 1;
+    const int ch_begin = first_of_quarter ? 0 : ch_half, ch_end = first_of_quarter ? ch_half : nchunks;
+    const int G = p.ostats ? p.Cout / p.ogs : 1;
+    const bool vec_ok = (p.Cout & 3) == 0;
+    const int L4 = p.Cout >> 2;                // float4 per output row (vector path)
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      const int q0 = (tile_begin + it) * kTileM;
+      const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
+      // ---- row bookkeeping (one thread per row)
+      if (et < kTileM) {
+        const int q = q0 + et;
+        int opix = -1, slot = 0;
+        if (q < p.Q) {
+          const uint32_t R = p.dPW.div((uint32_t)q);
+          const int x = q - (int)R * p.PW;
+          const int n = (int)p.dPH.div(R);
+          const int y = (int)R - n * p.PH;
+          bool valid = (x < p.W) && (y < p.H);
+          int yo = y, xo = x, Ho = p.H, Wo = p.W;
+          if (p.stride == 2) {
+            valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
+            yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+          }
+          if (valid && !(p.dbg & 8)) { opix = (n * Ho + yo) * Wo + xo; slot = n - n_lo; }
+        }
+        rowinfo[et] = make_int2(opix, slot);
+      }
+      // ---- pass 1: TMEM -> (+bias) -> staging
+      if (et == 0) DMD_TS(2, it, 0);
+      mbar_wait(tfull + b, ((uint32_t)it >> 1) & 1u);
+      if (et == 0) DMD_TS(2, it, 1);
+      tc_fence_after_sync();
+      {
+        const int row = quarter * 32 + lane;
+        const uint32_t trow = tmem_base + (uint32_t)b * kAccCols + ((uint32_t)(quarter * 32) << 16);
+        uint8_t* srow = sStage + (size_t)row * L.stage_pitch;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)ch * 16, v);
+          const float4* bp = reinterpret_cast<const float4*>(sbias + ch * 16);
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                  a += __shfl_xor_sync(0xffffffffu, a, off);
-                  bq += __shfl_xor_sync(0xffffffffu, bq, off);
-                }
-                if (lane == 0) {
-                  atomicAdd(p.ostats + ((size_t)img * G + grp) * 2, (double)a);
-                  atomicAdd(p.ostats + ((size_t)img * G + grp) * 2 + 1, (double)bq);
-                }
-              }
-            }
-            s = 0.f; ss = 0.f;
+          for (int i = 0; i < 4; ++i) {
+            const float4 bv = bp[i];
+            *reinterpret_cast<float4*>(srow + (size_t)(ch * 16 + 4 * i) * 4) =
+                make_float4(v[4 * i] + bv.x, v[4 * i + 1] + bv.y, v[4 * i + 2] + bv.z, v[4 * i + 3] + bv.w);
           }
         }
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + b);
+      if (lane == 0) mbar_arrive(tempty + b);   // TMEM accumulator may be overwritten
+      named_bar_sync(8, kEpiThreads);
+      if (et == 0) DMD_TS(2, it, 2);
+      // ---- pass 2: staging -> (+residual) -> coalesced global stores, GroupNorm partial sums
+      if (vec_ok) {
+        float s[kStatSlots] = {0.f, 0.f, 0.f}, ss[kStatSlots] = {0.f, 0.f, 0.f};
+        const int total4 = kTileM * L4;
+        for (int idx = et; idx < total4; idx += kEpiThreads) {
+          const int row = idx / L4, c4 = idx - row * L4;
+          const int2 ri = rowinfo[row];
+          if (ri.x >= 0) {
+            float4 v = *reinterpret_cast<const float4*>(sStage + (size_t)row * L.stage_pitch + (size_t)c4 * 16);
+            const size_t off = (size_t)ri.x * p.Cout + (size_t)c4 * 4;
+            if (p.resid) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + off));
+              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            *reinterpret_cast<float4*>(p.out + off) = v;
+            const float ps = (v.x + v.y) + (v.z + v.w);
+            const float pss = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+            for (int k = 0; k < kStatSlots; ++k) {
+              if (ri.y == k) { s[k] += ps; ss[k] += pss; }
+            }
+          }
+        }
+        if (p.ostats != nullptr) {
+          // host guarantees L4 in {4, 8, 16, 32} (so 256 % L4 == 0): a thread's channel quad, hence its group, is fixed
+          const int c4 = et % L4;
+          const int ogrp = (c4 * 4) / p.ogs;
+          const int lanes_per_group = p.ogs >> 2;   // lanes (float4s) covering one group inside a row
+          bool leader = true;
+#pragma unroll
+          for (int m = 1; m < 32; m <<= 1) {
+            // the xor-m partner lane is in the same group iff m stays inside the group span or jumps whole rows
+            const bool same = (m < lanes_per_group && m < L4) || (m >= L4);
+            if (same) {
+#pragma unroll
+              for (int k = 0; k < kStatSlots; ++k) {
+                s[k] += __shfl_xor_sync(0xffffffffu, s[k], m);
+                ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], m);
+              }
+              if (lane & m) leader = false;
+            }
+          }
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < kStatSlots; ++k) {
+              if (s[k] != 0.f || ss[k] != 0.f) {
+                atomicAdd(sstat + (k * kMaxOutGroups + ogrp) * 2, s[k]);
+                atomicAdd(sstat + (k * kMaxOutGroups + ogrp) * 2 + 1, ss[k]);
+              }
+            }
+          }
+        }
+      } else {
+        // narrow outputs (conv_out: 3 channels): scalar stores, no statistics
+        const int total = kTileM * p.Cout;
+        for (int idx = et; idx < total; idx += kEpiThreads) {
+          const int row = idx / p.Cout, c = idx - row * p.Cout;
+          const int2 ri = rowinfo[row];
+          if (ri.x >= 0) {
+            float v = *reinterpret_cast<const float*>(sStage + (size_t)row * L.stage_pitch + (size_t)c * 4);
+            const size_t off = (size_t)ri.x * p.Cout + c;
+            if (p.resid) v += __ldg(p.resid + off);
+            p.out[off] = v;
+          }
+        }
+      }
+      named_bar_sync(9, kEpiThreads);   // staging / rowinfo may be reused; sstat complete
+      if (p.ostats != nullptr && et < kStatSlots * G * 2) {
+        const int k = et / (G * 2), r = et - k * (G * 2);
+        const int ogrp = r >> 1, which = r & 1;
+        float* a = sstat + (k * kMaxOutGroups + ogrp) * 2 + which;
+        const float val = *a;
+        const int img = n_lo + k;
+        if (val != 0.f && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + ogrp) * 2 + which, (double)val);
+        *a = 0.f;
+      }
+      if (et == 0) DMD_TS(2, it, 3);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_free<2 * kAccCols>(tmem_base);
+  if (warp == mma_warp) tmem_free<2 * kAccCols>(tmem_base);
 }
 
 }  // namespace dmd

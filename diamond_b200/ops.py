@@ -64,7 +64,7 @@ def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: i
                  prologue: int = 0, silu: bool = False, stats0: Optional[Tensor] = None, stats1: Optional[Tensor] = None,
                  gs0: int = 0, gs1: int = 0, film: Optional[Tensor] = None, film_off: int = 0,
                  gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
-                 residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
+                 residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0, debug_buf: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
     _cuda(src0, src1, wpk, bias, stats0, stats1, film, gamma, beta, residual)
     b, hs, ws, c0 = src0.shape
     h, w = (2 * hs, 2 * ws) if upsample else (hs, ws)
@@ -81,6 +81,7 @@ def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: i
     d.gamma, d.beta, d.eps = _lib.ptr(gamma), _lib.ptr(beta), eps
     d.wpk, d.bias, d.Cout, d.CoutPad = wpk.data_ptr(), _lib.ptr(bias), cout, cout_pad
     d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
+    d.debug_buf = _lib.ptr(debug_buf)
     _lib.check(_lib.lib().dmd_conv2d_fprop(C.byref(d), _lib.current_stream()))
     return out, ostats
 

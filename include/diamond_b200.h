@@ -64,6 +64,7 @@ typedef struct dmd_conv_desc {
   double* out_stats;     /* [B][Cout/out_gs][2], accumulated (caller zeroes) or NULL */
   int out_gs;
   int debug;             /* bring-up only; 0 */
+  void* debug_buf;       /* bring-up only; NULL */
 } dmd_conv_desc;
 
 int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);

@@ -45,7 +45,13 @@ timeit("dbg skip loads+MMA", **F(dict(debug=6)))
 timeit("dbg skip loads+epilogue", **F(dict(debug=12)))
 timeit("dbg skip MMA+epilogue", **F(dict(debug=10)))
 timeit("dbg skip loads+MMA+epilogue (pure pipeline overhead)", **F(dict(debug=14)))
-timeit("1x1 conv 64->64 plain", prologue=0, silu=False, out_gs=0) if False else None
+timeit("skeleton + skip fence.proxy.async", **F(dict(debug=14 + 32)))
+timeit("skeleton + skip STS", **F(dict(debug=14 + 64)))
+timeit("skeleton + skip fence + STS", **F(dict(debug=14 + 96)))
+timeit("skeleton + skip tmem_ld", **F(dict(debug=14 + 128)))
+timeit("skeleton + skip fence+STS+tmem_ld", **F(dict(debug=14 + 224)))
+timeit("skeleton, no stats, skip fence+STS+tmem_ld", **F(dict(debug=14 + 224, out_gs=0)))
+timeit("skeleton no prologue, no stats, skip fence+STS+tmem_ld", prologue=0, silu=False, out_gs=0, debug=14 + 224)
 w1 = (torch.randn(64, 64, 1, 1) / 8).to(dev); wpk1, cp1 = ops.pack_conv_weight(w1, 64)
 def launch1(i): ops.conv2d_fprop(xs[i % 4], wpk1, 64, cp1, 64, 1, bias=bias)
 for i in range(3): launch1(i)
