@@ -80,6 +80,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
     if (d->prologue == 1) DMD_CHECK(d->film != nullptr, "conv: AdaGN prologue needs film");
     if (d->prologue == 2) DMD_CHECK(d->gamma && d->beta, "conv: GN prologue needs gamma/beta");
     DMD_CHECK(d->upsample == 0, "conv: prologue + upsample unsupported");
+    DMD_CHECK(d->C0 / d->gs0 + (d->C1 ? d->C1 / d->gs1 : 0) <= 4, "conv: at most 4 GroupNorm groups over the concatenated input");
   }
   p->st0 = d->stats0; p->st1 = d->stats1; p->gs0 = d->gs0 > 0 ? d->gs0 : 8; p->gs1 = d->gs1 > 0 ? d->gs1 : 8;
   p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off;

@@ -103,8 +103,8 @@ struct ConvSmemLayout {
 // barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], tmem slot
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
-  L.ctab_off = 512;  // [group 3][parity 2][a|b][slot 4][16 ch] floats
-  L.bias_off = L.ctab_off + kLoadGroups * 2 * 2 * kMaxImgSlots * 16 * 4;
+  L.ctab_off = 512;  // per group: [a|b][slot 4][kMaxCin] floats + [slot 4][4 groups][mean, rstd]
+  L.bias_off = L.ctab_off + kLoadGroups * (2 * kMaxImgSlots * kMaxCin + kMaxImgSlots * 4 * 2) * 4;
   L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
   L.sstat_off = L.rowinfo_off + kTileM * 8;          // [slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
@@ -181,17 +181,19 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
     const int grp = warp / WG;
     const int gt = tid - grp * GT;  // thread index inside the group
     const int total = my_tiles * kslabs;
-    float* my_ctab = ctab + (size_t)grp * (2 * 2 * kMaxImgSlots * 16);
+    float* tA = ctab + (size_t)grp * (2 * kMaxImgSlots * kMaxCin + kMaxImgSlots * 4 * 2);  // a[slot][kMaxCin]
+    float* tB = tA + kMaxImgSlots * kMaxCin;                                                // b[slot][kMaxCin]
+    float* tMR = tB + kMaxImgSlots * kMaxCin;                                               // (mean, rstd)[slot][4]
     int cur_it = -1, n_first = 0;
     int pix[kItemsPerThread];
     uint32_t meta = 0;       // per item: bit (8j) = valid pixel, bits (8j+1..8j+2) = image slot
-    uint32_t tab_parity = 0; // this group's coefficient table is double-buffered per slab
     int stage = grp % S;     // ring position of this group's first slab
     uint32_t phase = (uint32_t)(grp / S) & 1u;
     int it = 0, ks = grp;
     while (ks >= kslabs) { ks -= kslabs; ++it; }
     for (int g = grp; g < total; g += kLoadGroups) {
-      if (it != cur_it) {  // decode this thread's items for the new tile
+      const bool new_tile = (it != cur_it);
+      if (new_tile) {  // decode this thread's items for the new tile
         cur_it = it;
         const int qh0 = (tile_begin + it) * kTileM - halo;
         n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
@@ -229,24 +231,36 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
           v0[j] = __ldg(gp); v1[j] = __ldg(gp + 1);
         }
       }
-      // ---- coefficients of this slab's 16 channels for the (<= 4) images the tile touches, while the loads fly
-      float* tA = my_ctab + (size_t)tab_parity * (2 * kMaxImgSlots * 16);
-      float* tB = tA + kMaxImgSlots * 16;
-      if (p.pro != 0) {
-        if (gt < kMaxImgSlots * 16) {
-          const int slot = gt >> 4, c = ks * 16 + (gt & 15);
+      // ---- new tile: rebuild this group's GroupNorm/FiLM table (all channels, <= 4 images) while the loads fly.
+      //      fp64 only for the <= 16 (image, group) statistics; the per-channel part is fp32.
+      if (new_tile && p.pro != 0) {
+        named_bar_sync(1 + grp, GT);  // everyone in the group is done reading the previous tile's table
+        const int G0 = p.C0 / p.gs0, G1 = p.C1 ? p.C1 / p.gs1 : 0;
+        if (gt < kMaxImgSlots * 4) {
+          const int slot = gt >> 2, gi = gt & 3;
           const int n = n_first + slot;
-          float a = 0.f, bb = 0.f;
-          if (n < p.B && c < Ctot) {
-            const double* st;
-            int gs;
-            if (c < p.C0) { gs = p.gs0; st = p.st0 + ((size_t)n * (p.C0 / gs) + c / gs) * 2; }
-            else { gs = p.gs1; st = p.st1 + ((size_t)n * (p.C1 / gs) + (c - p.C0) / gs) * 2; }
-            const double cnt = (double)p.Hs * p.Ws * gs;
+          float mean_f = 0.f, rstd_f = 0.f;
+          if (n < p.B && gi < G0 + G1) {
+            const bool first = gi < G0;
+            const double* st = first ? p.st0 + ((size_t)n * G0 + gi) * 2 : p.st1 + ((size_t)n * G1 + (gi - G0)) * 2;
+            const double cnt = (double)p.Hs * p.Ws * (first ? p.gs0 : p.gs1);
             const double mean = st[0] / cnt;
             double var = st[1] / cnt - mean * mean;
             var = var > 0.0 ? var : 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+            mean_f = (float)mean;
+            rstd_f = (float)(1.0 / sqrt(var + (double)p.eps));
+          }
+          tMR[gt * 2] = mean_f;
+          tMR[gt * 2 + 1] = rstd_f;
+        }
+        named_bar_sync(1 + grp, GT);
+        for (int e = gt; e < kMaxImgSlots * Ctot; e += GT) {
+          const int slot = e / Ctot, c = e - slot * Ctot;
+          const int n = n_first + slot;
+          float a = 0.f, bb = 0.f;
+          if (n < p.B) {
+            const int gi = (c < p.C0) ? c / p.gs0 : G0 + (c - p.C0) / p.gs1;
+            const float mean = tMR[(slot * 4 + gi) * 2], rstd = tMR[(slot * 4 + gi) * 2 + 1];
             float sc, sh;
             if (p.pro == 1) {
               const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
@@ -257,10 +271,10 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
               sh = __ldg(p.beta + c);
             }
             a = rstd * sc;
-            bb = sh - (float)mean * a;
+            bb = sh - mean * a;
           }
-          tA[gt] = a;   // [slot][16]
-          tB[gt] = bb;
+          tA[slot * kMaxCin + c] = a;
+          tB[slot * kMaxCin + c] = bb;
         }
         named_bar_sync(1 + grp, GT);
       }
@@ -280,8 +294,8 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
             float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
             if (p.pro != 0) {
               const int slot = (int)((m >> 1) & 3u);
-              const float4* ca = reinterpret_cast<const float4*>(tA + slot * 16 + sub * 8);
-              const float4* cb = reinterpret_cast<const float4*>(tB + slot * 16 + sub * 8);
+              const float4* ca = reinterpret_cast<const float4*>(tA + slot * kMaxCin + ks * 16 + sub * 8);
+              const float4* cb = reinterpret_cast<const float4*>(tB + slot * kMaxCin + ks * 16 + sub * 8);
               const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
               v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
               v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
@@ -301,7 +315,6 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
       if (lane == 0) mbar_arrive(full + stage);
       if (gt == 0) DMD_TS(0, it, ks * 3 + 2);
       // advance by kLoadGroups slabs
-      tab_parity ^= 1u;
       ks += kLoadGroups;
       while (ks >= kslabs) { ks -= kslabs; ++it; }
       stage += kLoadGroups;
