@@ -106,9 +106,9 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, in
   L.ctab_off = 512;  // per group: [a|b][slot 4][kMaxCin] floats + [slot 4][4 groups][mean, rstd]
   L.bias_off = L.ctab_off + kLoadGroups * (2 * kMaxImgSlots * kMaxCin + kMaxImgSlots * 4 * 2) * 4;
   L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
-  L.sstat_off = L.rowinfo_off + kTileM * 8;          // [slot 3][group 4][2] floats
+  L.sstat_off = L.rowinfo_off + kTileM * 8;          // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
-  L.stage_off = (L.sstat_off + kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
+  L.stage_off = (L.sstat_off + kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
   L.w_off = (L.stage_off + kTileM * L.stage_pitch + 127u) & ~127u;
   const uint32_t w_bytes = (uint32_t)taps * Cin * CoutPad * 2;
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
   }
   if (warp == mma_warp) tmem_alloc<2 * kAccCols>(tmem_slot);
   for (int i = tid; i < 128; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
-  for (int i = tid; i < kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -484,13 +484,12 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
               if (lane & m) leader = false;
             }
           }
-          if (leader) {
+          if (leader) {  // exactly one leader lane per (warp, group): plain stores, summed in fixed order below
 #pragma unroll
             for (int k = 0; k < kStatSlots; ++k) {
-              if (s[k] != 0.f || ss[k] != 0.f) {
-                atomicAdd(sstat + (k * kMaxOutGroups + ogrp) * 2, s[k]);
-                atomicAdd(sstat + (k * kMaxOutGroups + ogrp) * 2 + 1, ss[k]);
-              }
+              float* dstp = sstat + (((size_t)ew * kStatSlots + k) * kMaxOutGroups + ogrp) * 2;
+              dstp[0] = s[k];
+              dstp[1] = ss[k];
             }
           }
         }
@@ -512,11 +511,11 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
       if (p.ostats != nullptr && et < kStatSlots * G * 2) {
         const int k = et / (G * 2), r = et - k * (G * 2);
         const int ogrp = r >> 1, which = r & 1;
-        float* a = sstat + (k * kMaxOutGroups + ogrp) * 2 + which;
-        const float val = *a;
+        double val = 0.0;
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) val += (double)sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + ogrp) * 2 + which];
         const int img = n_lo + k;
-        if (val != 0.f && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + ogrp) * 2 + which, (double)val);
-        *a = 0.f;
+        if (val != 0.0 && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + ogrp) * 2 + which, val);
       }
       if (et == 0) DMD_TS(2, it, 3);
     }

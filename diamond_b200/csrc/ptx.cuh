@@ -140,7 +140,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---------------------------------------------------------------- small math
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU with the bare SFU approximations (5 instructions): v * rcp(1 + 2^(-v*log2 e)).  ex2/rcp.approx.ftz carry ~2 ulp;
+// 1 + e >= 1 so rcp needs no range fix-up (e = +inf -> 0), unlike __fdividef / __expf which add ~4 instructions each.
+__device__ __forceinline__ float silu_f(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
