@@ -167,6 +167,28 @@ def workload_config(args, envs_override=None):
             "l2": "256 MiB L2 flush between timed steps (untimed)", "cuda_graph": True}
 
 
+def rank_inputs(envs: int, rank: int):
+    """Synthetic frame stacks / actions of one rank (weak scaling: every rank imagines its own envs)."""
+    O, inner, _ = build_oracle_model()
+    obs, act, _ = O.synthetic_inputs(envs, inner, 64, 64, 100 + rank)
+    return obs, act
+
+
+def max_over_ranks(values, device):
+    """Device timings are reduced with MAX over ranks (a multi-GPU step is as slow as its slowest rank)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(values, device=device, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def whole_job_value(frames_per_rank: int, world: int, ms: float) -> float:
+    return frames_per_rank * world / (ms * 1e-3)
+
+
 def conv_roofline(dev, envs, peaks, peaks_src):
     """Dominant kernel: conv_tc_kernel<64>, 3x3 64->64 at 64x64 (Appendix A row 2; 8 launches per forward + the 128->64
     and upsample variants share the code).  Timed live with CUDA events on the launching stream, rotating through
@@ -214,7 +236,9 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
     return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64, fused AdaGN+SiLU prologue, bias+stats epilogue",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            # dram__bytes_read+write per launch from profiles/r01_prof_conv_v3_summary.csv (that capture adds the residual read)
+            "traffic": 75.1e6, "algorithmic_bytes": (256 + 256) * 4096.0 * envs,
             "us_per_launch": ms * 1e3, "flop_per_launch": flops, "peak_source": peaks_src + " bf16 burst (fp16 and bf16 share the tensor-pipe rate)"}
 
 
@@ -244,7 +268,7 @@ def run_native(args):
     den = den.to(dev).eval()
     sampler = DiffusionSampler(den, DiffusionSamplerConfig(3))
     B = args.envs
-    obs, act, _ = O.synthetic_inputs(B, inner, 64, 64, 100 + rank)
+    obs, act = rank_inputs(B, rank)
     obs_d, act_d = obs.to(dev), act.to(dev)
     obs_h, act_h = obs.pin_memory(), act.pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -292,10 +316,7 @@ def run_native(args):
     clocks = clk.finish()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
 
-    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms], dev)
     frames = B * args.steps * world
     if rank == 0:
         peaks, peaks_src = load_peaks()
@@ -306,7 +327,7 @@ def run_native(args):
             cpu_val, cpu_times = cpu_frames_per_s(cpu_envs, 3, cores)
         else:
             cores, avail, cpu_val = 0, 0, None
-        value = frames / (dev_ms * 1e-3)
+        value = whole_job_value(B * args.steps, world, dev_ms)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,67 @@
+"""CPU: host-side mirror of the reference's module surface (no kernel launches)."""
+import pytest
+import torch
+
+from diamond_b200.models.diffusion import (Denoiser, DenoiserConfig, DiffusionSamplerConfig, InnerModelConfig)
+from diamond_b200.models.diffusion.diffusion_sampler import build_sigmas
+from oracle import ref_import
+from oracle import torch_oracle as O
+
+
+def _denoiser(inner: O.InnerCfg) -> Denoiser:
+    return Denoiser(DenoiserConfig(InnerModelConfig(inner.img_channels, inner.num_steps_conditioning, inner.cond_channels,
+                                                    list(inner.depths), list(inner.channels), list(inner.attn_depths),
+                                                    inner.num_actions), 0.5, 0.3))
+
+
+@pytest.mark.parametrize("inner", [O.InnerCfg(), O.InnerCfg(depths=[1, 2, 1], channels=[32, 64, 32], attn_depths=[0, 0, 1],
+                                                             cond_channels=64, num_steps_conditioning=2, num_actions=6)])
+def test_state_dict_keys_and_shapes_match_the_reference_layout(inner):
+    den = _denoiser(inner)
+    want = O.inner_model_shapes(inner)
+    got = [(k, tuple(v.shape)) for k, v in den.inner_model.state_dict().items()]
+    assert got == want
+    if ref_import.available():
+        ns = ref_import.load()
+        D = ns.diffusion
+        ref = D.Denoiser(D.DenoiserConfig(D.InnerModelConfig(inner.img_channels, inner.num_steps_conditioning, inner.cond_channels,
+                                                             list(inner.depths), list(inner.channels), list(inner.attn_depths),
+                                                             inner.num_actions), 0.5, 0.3))
+        assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == [(k, tuple(v.shape)) for k, v in den.state_dict().items()]
+
+
+def test_default_denoiser_has_the_reference_parameter_count_and_init():
+    den = _denoiser(O.InnerCfg())
+    assert sum(p.numel() for p in den.parameters()) == 4_405_955
+    sd = den.inner_model.state_dict()
+    # zero-initialised layers (blocks.py:59-60,139; inner_model.py:42)
+    assert float(sd["conv_out.weight"].abs().sum()) == 0
+    assert float(sd["unet.d_blocks.0.resblocks.0.conv2.weight"].abs().sum()) == 0
+    assert float(sd["unet.mid_blocks.resblocks.0.attn.out_proj.weight"].abs().sum()) == 0
+    w = sd["unet.downsamples.1.conv.weight"].flatten(1)  # orthogonal (blocks.py:97)
+    assert torch.allclose(w @ w.t(), torch.eye(64), atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree absent")
+def test_reference_configure_opt_accepts_the_mirror():
+    """utils.configure_opt classifies parameters by isinstance(owner, nn.Conv2d/Linear/GroupNorm/...) and asserts full
+    coverage (utils.py:129-166): expected split for the denoiser is 114 decay / 121 no-decay."""
+    ns = ref_import.load()
+    den = _denoiser(O.InnerCfg())
+    opt = ns.utils.configure_opt(den, 1e-4, 1e-2, 1e-8)
+    assert [len(g["params"]) for g in opt.param_groups] == [114, 121]
+
+
+def test_sigma_schedule_matches_reference_values():
+    s = build_sigmas(3, 2e-3, 5, 7, torch.device("cpu"))
+    assert torch.allclose(s, torch.tensor([5.0, 0.28308, 0.002, 0.0]), atol=1e-5)
+    assert torch.equal(s, O.build_sigmas(3, 2e-3, 5, 7))
+    assert DiffusionSamplerConfig(3).order == 1
+
+
+def test_training_forward_is_explicitly_unbuilt_and_cpu_is_rejected():
+    den = _denoiser(O.InnerCfg())
+    with pytest.raises(NotImplementedError):
+        den(None)
+    with pytest.raises(RuntimeError):  # no CPU fallback: the native executor refuses non-CUDA parameters
+        den.denoise(torch.zeros(1, 3, 64, 64), torch.ones(1), torch.zeros(1, 12, 64, 64), torch.zeros(1, 4, dtype=torch.long))
