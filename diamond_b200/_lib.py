@@ -29,6 +29,13 @@ class DenoiserConfigC(C.Structure):
     ]
 
 
+class ActorCriticConfigC(C.Structure):
+    _fields_ = [
+        ("lstm_dim", _i), ("img_channels", _i), ("img_size", _i), ("num_levels", _i),
+        ("channels", _i * DMD_MAX_LEVELS), ("down", _i * DMD_MAX_LEVELS), ("num_actions", _i),
+    ]
+
+
 class SamplerConfigC(C.Structure):
     _fields_ = [
         ("num_sigmas", _i), ("sigmas_host", C.POINTER(_f)), ("order", _i),
@@ -56,6 +63,13 @@ SIGNATURES = {
     "dmd_denoiser_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmd_inner_model_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmd_sampler_sample": (_i, [_vp, C.POINTER(SamplerConfigC), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dmd_actor_critic_create": (_vp, [C.POINTER(ActorCriticConfigC)]),
+    "dmd_actor_critic_destroy": (None, [_vp]),
+    "dmd_actor_critic_num_tensors": (_i, [_vp]),
+    "dmd_actor_critic_packed_bytes": (_sz, [_vp]),
+    "dmd_actor_critic_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp]),
+    "dmd_actor_critic_workspace_bytes": (_sz, [_vp, _i]),
+    "dmd_actor_critic_forward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -194,10 +194,12 @@ static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
   return 0;
 }
 
-static int linear_launch(const float* in, const float* W, const float* bias, float* out, int B, int K, int F, int silu, cudaStream_t st) {
-  DMD_CHECK(K % 4 == 0 && K <= 256, "linear: K=%d must be a multiple of 4 and <= 256", K);
+static int linear_launch(const float* in, const float* W, const float* bias, float* out, int B, int K, int F, int silu, cudaStream_t st,
+                         int accumulate = 0, int hw_perm = 0) {
+  DMD_CHECK(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
+  DMD_CHECK(hw_perm == 0 || K % hw_perm == 0, "linear: bad hw_perm");
   if (init_kernels()) return 1;
-  linear_kernel<<<dim3((F + 31) / 32, (B + 31) / 32), 256, (size_t)64 * K * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu);
+  linear_kernel<<<dim3((F + 31) / 32, (B + 31) / 32), 256, (size_t)64 * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -720,5 +722,169 @@ extern "C" int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc,
   }
   DMD_CUDA(cudaMemcpyAsync(out_x, pl.s_x[0], img_elems * 4, cudaMemcpyDeviceToDevice, st));
   if (out_traj) DMD_CUDA(cudaMemcpyAsync(out_traj, pl.s_traj, traj_bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- actor-critic executor
+struct dmd_actor_critic {
+  dmd_actor_critic_config cfg;
+  int n_tensors = 0;
+  struct Level { int cin, cout, down; int gn_w, gn_b; ConvW conv; int has_skip; ConvW skip; };
+  ConvW conv0;
+  std::vector<Level> levels;
+  int i_wih = 0, i_whh = 0, i_bih = 0, i_bhh = 0, i_cw = 0, i_cb = 0, i_aw = 0, i_ab = 0;
+  int feat_c = 0, feat_hw = 0;
+  size_t packed_bytes = 0;
+  std::vector<const float*> ptrs;
+  uint8_t* packed = nullptr;
+};
+
+namespace {
+
+ConvW ac_conv(int& idx, size_t& pk, int cout, int cin_real, int taps, int c0_store) {
+  ConvW c; c.w_idx = idx++; c.b_idx = idx++;
+  c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
+  c.c0_real = cin_real; c.c0_store = c0_store; c.Cin = round_up(c0_store, 16);
+  c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2; pk = (pk + 255) & ~(size_t)255;
+  return c;
+}
+
+struct AcBuffers {
+  float* x0; std::vector<float*> r, y, pooled; std::vector<double*> st_in, st_y; float *gates, *hx, *cx; double* stats; size_t stats_bytes; size_t total;
+};
+
+// lays out the workspace; base may be null (size query)
+int ac_layout(const dmd_actor_critic* h, int B, uint8_t* base, AcBuffers* o) {
+  const dmd_actor_critic_config& c = h->cfg;
+  Bump sb{base};
+  const size_t nl = h->levels.size();
+  o->st_in.resize(nl + 1); o->st_y.resize(nl);
+  int S = c.img_size;
+  // statistics first (one memset)
+  for (size_t i = 0; i <= nl; ++i) {
+    const int C = i == 0 ? c.channels[0] : h->levels[i - 1].cout;
+    o->st_in[i] = (double*)sb.take((size_t)B * (C / gn_group_size(C)) * 2 * 8);
+  }
+  o->stats = (double*)base; o->stats_bytes = (sb.off + 255) & ~(size_t)255;
+  Bump bb{base ? base + o->stats_bytes : nullptr};
+  o->x0 = (float*)bb.take((size_t)B * S * S * h->conv0.c0_store * 4);
+  float* cur = (float*)bb.take((size_t)B * S * S * c.channels[0] * 4);  // conv0 output
+  o->r.assign(nl, nullptr); o->y.assign(nl, nullptr); o->pooled.assign(nl + 1, nullptr);
+  o->pooled[0] = cur;
+  for (size_t i = 0; i < nl; ++i) {
+    const auto& lv = h->levels[i];
+    if (lv.has_skip) o->r[i] = (float*)bb.take((size_t)B * S * S * lv.cout * 4);
+    o->y[i] = (float*)bb.take((size_t)B * S * S * lv.cout * 4);
+    if (lv.down) { S /= 2; o->pooled[i + 1] = (float*)bb.take((size_t)B * S * S * lv.cout * 4); }
+    else o->pooled[i + 1] = o->y[i];
+  }
+  o->gates = (float*)bb.take((size_t)B * 4 * c.lstm_dim * 4);
+  o->total = o->stats_bytes + bb.off + 256;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" dmd_actor_critic* dmd_actor_critic_create(const dmd_actor_critic_config* cfg) {
+  if (!cfg || cfg->num_levels < 1 || cfg->num_levels > DMD_MAX_LEVELS) { fail("actor_critic_create: bad config"); return nullptr; }
+  for (int i = 0; i < cfg->num_levels; ++i)
+    if (cfg->channels[i] % 32 || cfg->channels[i] > 64) { fail("actor_critic_create: channels must be 32 or 64 (got %d)", cfg->channels[i]); return nullptr; }
+  if (cfg->lstm_dim % 4) { fail("actor_critic_create: lstm_dim must be a multiple of 4"); return nullptr; }
+  if (init_kernels()) return nullptr;
+  dmd_actor_critic* h = new dmd_actor_critic();
+  h->cfg = *cfg;
+  int idx = 0; size_t pk = 0;
+  // registration order (actor_critic.py:41-47,101-110): encoder.encoder.{0: Conv3x3, k: SmallResBlock(f.0.norm, f.2, skip_projection),
+  // MaxPool...}, lstm.{weight_ih, weight_hh, bias_ih, bias_hh}, critic_linear, actor_linear
+  h->conv0 = ac_conv(idx, pk, cfg->channels[0], cfg->img_channels, 9, round_up(cfg->img_channels, 8));
+  int S = cfg->img_size;
+  for (int i = 0; i < cfg->num_levels; ++i) {
+    dmd_actor_critic::Level lv;
+    lv.cin = cfg->channels[i > 0 ? i - 1 : 0]; lv.cout = cfg->channels[i]; lv.down = cfg->down[i] ? 1 : 0;
+    lv.gn_w = idx++; lv.gn_b = idx++;
+    lv.conv = ac_conv(idx, pk, lv.cout, lv.cin, 9, lv.cin);
+    lv.has_skip = lv.cin != lv.cout;
+    if (lv.has_skip) lv.skip = ac_conv(idx, pk, lv.cout, lv.cin, 1, lv.cin);
+    h->levels.push_back(lv);
+    if (lv.down) S /= 2;
+  }
+  h->feat_c = cfg->channels[cfg->num_levels - 1]; h->feat_hw = S * S;
+  h->i_wih = idx++; h->i_whh = idx++; h->i_bih = idx++; h->i_bhh = idx++;
+  h->i_cw = idx++; h->i_cb = idx++; h->i_aw = idx++; h->i_ab = idx++;
+  h->n_tensors = idx; h->packed_bytes = pk + 256;
+  return h;
+}
+extern "C" void dmd_actor_critic_destroy(dmd_actor_critic* h) { delete h; }
+extern "C" int dmd_actor_critic_num_tensors(const dmd_actor_critic* h) { return h->n_tensors; }
+extern "C" size_t dmd_actor_critic_packed_bytes(const dmd_actor_critic* h) { return h->packed_bytes; }
+
+extern "C" int dmd_actor_critic_set_weights(dmd_actor_critic* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream) {
+  DMD_CHECK(h && ptrs_host && packed, "ac set_weights: null argument");
+  DMD_CHECK(n_ptrs == h->n_tensors, "ac set_weights: expected %d tensors (ActorCritic.state_dict order), got %d", h->n_tensors, n_ptrs);
+  h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
+  h->packed = (uint8_t*)packed;
+  auto pack = [&](const ConvW& c) {
+    return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, stream);
+  };
+  if (pack(h->conv0)) return 1;
+  for (auto& lv : h->levels) { if (pack(lv.conv)) return 1; if (lv.has_skip && pack(lv.skip)) return 1; }
+  return 0;
+}
+
+extern "C" size_t dmd_actor_critic_workspace_bytes(const dmd_actor_critic* h, int B) {
+  AcBuffers b; ac_layout(h, B, nullptr, &b); return b.total;
+}
+
+extern "C" int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float* obs, const float* hx_in, const float* cx_in,
+                                        float* logits, float* val, float* hx_out, float* cx_out, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  DMD_CHECK(h && obs && hx_in && cx_in && logits && val && hx_out && cx_out && workspace, "ac forward: null argument");
+  DMD_CHECK(!h->ptrs.empty() && h->packed, "ac forward: call dmd_actor_critic_set_weights first");
+  DMD_CHECK(((uintptr_t)workspace & 255) == 0, "ac forward: workspace must be 256-byte aligned");
+  const dmd_actor_critic_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  AcBuffers b; ac_layout(h, B, (uint8_t*)workspace, &b);
+  DMD_CHECK(workspace_bytes >= b.total, "ac forward: workspace too small (%zu < %zu)", workspace_bytes, b.total);
+  DMD_CUDA(cudaMemsetAsync(b.stats, 0, b.stats_bytes, st));
+  int S = c.img_size;
+  if (dmd_nchw_to_nhwc(obs, b.x0, B, c.img_channels, h->conv0.c0_store, S * S, st)) return 1;
+  auto run_conv = [&](const ConvW& cw, const float* src, int Csrc, int hw, int pro, int gamma_idx, int beta_idx, const double* st_in,
+                      const float* resid, float* out, double* st_out) -> int {
+    dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = src; d.C0 = Csrc; d.Cin = cw.Cin; d.B = B; d.Hs = hw; d.Ws = hw; d.taps = cw.taps; d.stride = 1;
+    d.prologue = pro; d.silu = pro ? 1 : 0; d.stats0 = st_in; d.gs0 = pro ? gn_group_size(Csrc) : 0;
+    if (pro) { d.gamma = h->ptrs[gamma_idx]; d.beta = h->ptrs[beta_idx]; }
+    d.eps = kGnEps; d.wpk = h->packed + cw.pk_off; d.bias = h->ptrs[cw.b_idx]; d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
+    d.residual = resid; d.out = out; d.out_stats = st_out; d.out_gs = gn_group_size(cw.Cout);
+    ConvParams p; size_t smem; int cols;
+    if (conv_fill(&d, &p, &smem, &cols)) return 1;
+    return conv_launch(p, smem, cols, st);
+  };
+  // conv0 feeds the first GroupNorm -> statistics in its epilogue
+  if (run_conv(h->conv0, b.x0, h->conv0.c0_store, S, 0, 0, 0, nullptr, nullptr, b.pooled[0], b.st_in[0])) return 1;
+  for (size_t i = 0; i < h->levels.size(); ++i) {
+    const auto& lv = h->levels[i];
+    const float* x = b.pooled[i];
+    const float* r = x;
+    if (lv.has_skip) { if (run_conv(lv.skip, x, lv.cin, S, 0, 0, 0, nullptr, nullptr, b.r[i], nullptr)) return 1; r = b.r[i]; }
+    // SmallResBlock: skip(x) + conv3x3(silu(GroupNorm(x)))  (blocks.py:122-123)
+    double* st_y = lv.down ? nullptr : b.st_in[i + 1];
+    if (run_conv(lv.conv, x, lv.cin, S, 2, lv.gn_w, lv.gn_b, b.st_in[i], r, b.y[i], st_y)) return 1;
+    if (lv.down) {
+      const int total = (S / 2) * (S / 2) * lv.cout;
+      maxpool2_stats_kernel<<<dim3((total + 255) / 256, B), 256, 0, st>>>(b.y[i], b.pooled[i + 1], i + 1 < h->levels.size() ? b.st_in[i + 1] : nullptr,
+                                                                         S, S, lv.cout, gn_group_size(lv.cout));
+      DMD_LAUNCH_OK();
+      S /= 2;
+    }
+  }
+  const float* feat = b.pooled[h->levels.size()];
+  const int K = h->feat_c * h->feat_hw, D = c.lstm_dim;
+  if (linear_launch(feat, h->ptrs[h->i_wih], h->ptrs[h->i_bih], b.gates, B, K, 4 * D, 0, st, 0, h->feat_hw)) return 1;
+  if (linear_launch(hx_in, h->ptrs[h->i_whh], h->ptrs[h->i_bhh], b.gates, B, D, 4 * D, 0, st, 1, 0)) return 1;
+  lstm_gates_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(b.gates, cx_in, hx_out, cx_out, B, D);
+  DMD_LAUNCH_OK();
+  if (linear_launch(hx_out, h->ptrs[h->i_aw], h->ptrs[h->i_ab], logits, B, D, c.num_actions, 0, st)) return 1;
+  if (linear_launch(hx_out, h->ptrs[h->i_cw], h->ptrs[h->i_cb], val, B, D, 1, 0, st)) return 1;
   return 0;
 }

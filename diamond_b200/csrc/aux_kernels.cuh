@@ -84,38 +84,50 @@ __global__ void cond_embed_kernel(const float* __restrict__ cs, const int64_t* _
   e[i] = __fadd_rn(four, act_emb[(size_t)a * E + (k % E)]);
 }
 
-// out[n][f] = act( sum_k in[n][k] * W[f][k] + b[f] ),  K multiple of 4 and <= 256.
+// out[n][f] (+)= act( sum_k in[n][k] * W[f][k] + b[f] ),  K multiple of 4; K is processed in chunks of <= 256.
 // grid (ceil(F/32), ceil(B/32)), 256 threads: warp w owns rows f = 4w..4w+3 of the 32-row tile, lane = sample n.
+// hw_perm > 0: `in` is an NHWC tensor [B][hw_perm][K/hw_perm] read in NCHW-flatten order (k = c*hw + pix), i.e. the
+// x.flatten(start_dim=1) of actor_critic.py:71 without materialising the permutation.
+constexpr int kLinChunk = 256;
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                      const float* __restrict__ bias, float* __restrict__ out, int B,
-                                                     int K, int F, int silu) {
+                                                     int K, int F, int silu, int accumulate, int hw_perm) {
   extern __shared__ __align__(16) float sm_lin[];
-  float* Ws = sm_lin;            // [32][K]
-  float* inT = sm_lin + 32 * K;  // [K][32]
+  float* Ws = sm_lin;                    // [32][kLinChunk]
+  float* inT = sm_lin + 32 * kLinChunk;  // [kLinChunk][32]
   const int f0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tid = threadIdx.x;
-  const int K4 = K >> 2;
-  for (int i = tid; i < 32 * K4; i += 256) {
-    const int r = i / K4, c4 = i - r * K4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f0 + r < F) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(f0 + r) * K) + c4);
-    reinterpret_cast<float4*>(Ws + r * K)[c4] = v;
-  }
-  for (int i = tid; i < 32 * K; i += 256) {
-    const int nn = i / K, k = i - nn * K;
-    inT[k * 32 + nn] = (n0 + nn < B) ? in[(size_t)(n0 + nn) * K + k] : 0.f;
-  }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k4 = 0; k4 < K4; ++k4) {
-    const float x0 = inT[(4 * k4 + 0) * 32 + lane], x1 = inT[(4 * k4 + 1) * 32 + lane];
-    const float x2 = inT[(4 * k4 + 2) * 32 + lane], x3 = inT[(4 * k4 + 3) * 32 + lane];
+  for (int k0 = 0; k0 < K; k0 += kLinChunk) {
+    const int kc = min(kLinChunk, K - k0), kc4 = kc >> 2;
+    __syncthreads();
+    for (int i = tid; i < 32 * kc4; i += 256) {
+      const int r = i / kc4, c4 = i - r * kc4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f0 + r < F) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(f0 + r) * K + k0) + c4);
+      reinterpret_cast<float4*>(Ws + r * kLinChunk)[c4] = v;
+    }
+    for (int i = tid; i < 32 * kc; i += 256) {
+      const int nn = i / kc, k = i - nn * kc;
+      float v = 0.f;
+      if (n0 + nn < B) {
+        const int kk = k0 + k;
+        if (hw_perm > 0) { const int c = kk / hw_perm, pix = kk - c * hw_perm; v = in[(size_t)(n0 + nn) * K + (size_t)pix * (K / hw_perm) + c]; }
+        else v = in[(size_t)(n0 + nn) * K + kk];
+      }
+      inT[k * 32 + nn] = v;
+    }
+    __syncthreads();
+    for (int k4 = 0; k4 < kc4; ++k4) {
+      const float x0 = inT[(4 * k4 + 0) * 32 + lane], x1 = inT[(4 * k4 + 1) * 32 + lane];
+      const float x2 = inT[(4 * k4 + 2) * 32 + lane], x3 = inT[(4 * k4 + 3) * 32 + lane];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 w = reinterpret_cast<const float4*>(Ws + (warp * 4 + j) * K)[k4];
-      acc[j] = fmaf(w.x, x0, acc[j]); acc[j] = fmaf(w.y, x1, acc[j]);
-      acc[j] = fmaf(w.z, x2, acc[j]); acc[j] = fmaf(w.w, x3, acc[j]);
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = reinterpret_cast<const float4*>(Ws + (warp * 4 + j) * kLinChunk)[k4];
+        acc[j] = fmaf(w.x, x0, acc[j]); acc[j] = fmaf(w.y, x1, acc[j]);
+        acc[j] = fmaf(w.z, x2, acc[j]); acc[j] = fmaf(w.w, x3, acc[j]);
+      }
     }
   }
   if (n0 + lane < B) {
@@ -123,12 +135,63 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
     for (int j = 0; j < 4; ++j) {
       const int f = f0 + warp * 4 + j;
       if (f < F) {
-        float v = acc[j] + bias[f];
+        float v = acc[j] + (bias ? bias[f] : 0.f);
+        float* o = out + (size_t)(n0 + lane) * F + f;
+        if (accumulate) v += *o;
         if (silu) v = v / (1.0f + expf(-v));
-        out[(size_t)(n0 + lane) * F + f] = v;
+        *o = v;
       }
     }
   }
+}
+
+// MaxPool2d(2) (actor_critic.py:109) on NHWC + GroupNorm partial sums of the pooled tensor (input of the next
+// SmallResBlock's GroupNorm).  grid (ceil(Ho*Wo*C/256), B)
+__global__ void maxpool2_stats_kernel(const float* __restrict__ x, float* __restrict__ y, double* __restrict__ stats,
+                                      int H, int W, int C, int gs) {
+  const int n = blockIdx.y;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = Ho * Wo * C;
+  float v = 0.f;
+  int c = 0;
+  const bool ok = i < total;
+  if (ok) {
+    c = i % C;
+    const int pix = i / C, xo = pix % Wo, yo = pix / Wo;
+    const float* p = x + (((size_t)n * H + 2 * yo) * W + 2 * xo) * C + c;
+    v = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(size_t)W * C], p[(size_t)W * C + C]));
+    y[(size_t)n * total + i] = v;
+  }
+  if (stats != nullptr) {
+    // lanes of a warp hold consecutive channels; gs is a multiple of 32 or divides 32 -> reduce within aligned segments
+    const int G = C / gs;
+    float s = ok ? v : 0.f, ss = ok ? v * v : 0.f;
+    const int seg = gs < 32 ? gs : 32;  // C % seg == 0 and warps start at multiples of 32 channels-wise (256 % C == 0 or C % 32 == 0)
+    for (int off = seg >> 1; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (ok && (threadIdx.x & (seg - 1)) == 0) {
+      atomicAdd(stats + ((size_t)n * G + c / gs) * 2, (double)s);
+      atomicAdd(stats + ((size_t)n * G + c / gs) * 2 + 1, (double)ss);
+    }
+  }
+}
+
+// LSTMCell pointwise part (torch gate order i, f, g, o; actor_critic.py:72): gates [B][4H] already hold
+// x W_ih^T + b_ih + h W_hh^T + b_hh.
+__global__ void lstm_gates_kernel(const float* __restrict__ gates, const float* __restrict__ c_in, float* __restrict__ h_out,
+                                  float* __restrict__ c_out, int B, int Hd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Hd) return;
+  const int n = i / Hd, j = i - n * Hd;
+  const float* g = gates + (size_t)n * 4 * Hd;
+  const float ig = 1.f / (1.f + expf(-g[j])), fg = 1.f / (1.f + expf(-g[Hd + j]));
+  const float gg = tanhf(g[2 * Hd + j]), og = 1.f / (1.f + expf(-g[3 * Hd + j]));
+  const float c = fg * c_in[i] + ig * gg;
+  c_out[i] = c;
+  h_out[i] = og * tanhf(c);
 }
 
 // ------------------------------------------------------------------------------------------------

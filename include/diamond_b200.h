@@ -140,6 +140,34 @@ int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int
                        const int64_t* prev_act, const float* x0, const float* eps, float* out_x, float* out_traj,
                        void* workspace, size_t workspace_bytes, int use_graph, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Actor-critic executor: ActorCritic.predict_act_value (src/models/actor_critic.py:68-73) = ActorCriticEncoder
+ * (:101-113: Conv3x3 + [SmallResBlock (blocks.py:116-123), MaxPool2d]*) -> flatten -> LSTMCell -> actor / critic heads.
+ * Inference (no autograd) only in this round.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct dmd_actor_critic_config {
+  int lstm_dim;
+  int img_channels;
+  int img_size;
+  int num_levels;
+  int channels[DMD_MAX_LEVELS];
+  int down[DMD_MAX_LEVELS];
+  int num_actions;
+} dmd_actor_critic_config;
+
+typedef struct dmd_actor_critic dmd_actor_critic;
+
+dmd_actor_critic* dmd_actor_critic_create(const dmd_actor_critic_config* cfg);
+void dmd_actor_critic_destroy(dmd_actor_critic* h);
+int dmd_actor_critic_num_tensors(const dmd_actor_critic* h);          /* == len(ActorCritic.state_dict()) */
+size_t dmd_actor_critic_packed_bytes(const dmd_actor_critic* h);
+int dmd_actor_critic_set_weights(dmd_actor_critic* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream);
+size_t dmd_actor_critic_workspace_bytes(const dmd_actor_critic* h, int B);
+/* obs (B,C,S,S) NCHW; hx_in/cx_in (B,lstm_dim); outputs: logits (B,A), val (B), hx_out/cx_out (B,lstm_dim). */
+int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float* obs, const float* hx_in, const float* cx_in,
+                             float* logits, float* val, float* hx_out, float* cx_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,5 +98,32 @@ def main():
               "size", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def make_actor_critic():
+    """Reference ActorCritic.predict_act_value over 3 recurrent steps (hidden state carried), seeded de-zeroed weights."""
+    ns = ref_import.load()
+    AC = ns.actor_critic
+    cfg = O.ActorCriticCfg()
+    sd = O.seeded_actor_critic_state_dict(cfg, 555)
+    ac = AC.ActorCritic(AC.ActorCriticConfig(cfg.lstm_dim, cfg.img_channels, cfg.img_size, list(cfg.channels), list(cfg.down), cfg.num_actions)).eval()
+    assert [(k, tuple(v.shape)) for k, v in ac.state_dict().items()] == O.actor_critic_shapes(cfg)
+    ac.load_state_dict(sd)
+    rng = np.random.default_rng(91)
+    b = 5
+    obs = torch.from_numpy(rng.integers(0, 256, size=(3, b, 3, 64, 64)).astype(np.float32)).div(255).mul(2).sub(1)
+    hx = torch.from_numpy(rng.standard_normal((b, 512)).astype(np.float32)) * 0.3
+    cx = torch.from_numpy(rng.standard_normal((b, 512)).astype(np.float32)) * 0.3
+    logits, vals = [], []
+    h, c = hx, cx
+    with torch.no_grad():
+        for t in range(3):
+            out = ac.predict_act_value(obs[t], (h, c))
+            logits.append(out.logits_act); vals.append(out.val); h, c = out.hx_cx
+    np.savez_compressed(os.path.join(OUT, "actor_critic_default.npz"), weights_checksum=np.float64(O.state_checksum(sd)),
+                        hx0=hx.numpy(), cx0=cx.numpy(), logits=torch.stack(logits).numpy(), val=torch.stack(vals).numpy(),
+                        hx=h.numpy(), cx=c.numpy())
+    print("actor_critic_default logits rms", float(torch.stack(logits).pow(2).mean().sqrt()))
+
+
 if __name__ == "__main__":
     main()
+    make_actor_critic()

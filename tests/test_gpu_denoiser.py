@@ -181,3 +181,47 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdiamond_b200.so")
     with pytest.raises(_lib.LibraryMissing):
         _lib.lib()
+
+
+def test_world_model_env_runs_on_native_sampler():
+    """WorldModelEnv.step drives the native sampler: the next frame equals a direct sample() on the same buffers and
+    lies on the uint8 grid after the final Euler step (x ~= denoised, diffusion_sampler.py:47-49)."""
+    dev = _dev()
+    from types import SimpleNamespace
+
+    from diamond_b200.envs import WorldModelEnv, WorldModelEnvConfig
+    from diamond_b200.models.diffusion import DiffusionSamplerConfig
+    from oracle import torch_oracle as O
+
+    inner = O.InnerCfg(depths=[1, 1, 1, 1])
+    den, _ = _build(inner, 77, dev)
+
+    class RewEnd:
+        def predict_rew_end(self, obs, act, next_obs, hx_cx=None):
+            b, t = obs.shape[:2]
+            hx = torch.zeros(1, b, 8, device=obs.device) if hx_cx is None else hx_cx[0] + 1
+            return torch.zeros(b, t, 3, device=obs.device), torch.tensor([4.0, -4.0], device=obs.device).expand(b, t, 2), (hx, hx.clone())
+
+    class Loader:
+        batch_sampler = SimpleNamespace(batch_size=4)
+
+        def __iter__(self):
+            g = torch.Generator().manual_seed(0)
+            while True:
+                yield SimpleNamespace(obs=torch.rand(4, 5, 3, 64, 64, generator=g) * 2 - 1, act=torch.randint(0, 4, (4, 5), generator=g))
+
+    env = WorldModelEnv(den, RewEnd(), Loader(), WorldModelEnvConfig(3, 2, DiffusionSamplerConfig(3)))
+    obs0, _ = env.reset()
+    assert obs0.shape == (4, 3, 64, 64) and obs0.is_cuda
+    for step in range(4):
+        before_obs, before_act = env.obs_buffer.clone(), env.act_buffer.clone()
+        act = torch.randint(0, 4, (4,), device=dev)
+        torch.manual_seed(100 + step)
+        obs, rew, end, trunc, info = env.step(act)
+        before_act[:, -1] = act
+        torch.manual_seed(100 + step)
+        want, _ = env.sampler.sample(before_obs, before_act)
+        alive = ~torch.logical_or(end, trunc).bool()
+        assert float((obs[alive] != want[alive]).float().mean()) < 1e-3
+        assert obs.abs().max() <= 1.0 + 1e-5
+        assert torch.equal(trunc.cpu(), torch.full((4,), int(step == 2)))
