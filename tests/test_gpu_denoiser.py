@@ -222,6 +222,7 @@ def test_world_model_env_runs_on_native_sampler():
         torch.manual_seed(100 + step)
         want, _ = env.sampler.sample(before_obs, before_act)
         alive = ~torch.logical_or(end, trunc).bool()
-        assert float((obs[alive] != want[alive]).float().mean()) < 1e-3
+        if alive.any():
+            assert float((obs[alive] != want[alive]).float().mean()) < 1e-3
         assert obs.abs().max() <= 1.0 + 1e-5
         assert torch.equal(trunc.cpu(), torch.full((4,), int(step == 2)))
