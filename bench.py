@@ -201,44 +201,55 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
     wpk, cp = ops.pack_conv_weight(wt, 64)
     bias = torch.zeros(64, device=dev)
-    nset = 6  # 6 x (in + out) x 33.5 MB at 32 envs  > 126 MB L2
+    nset = 6  # rotating operand / output sets: 6 x (17 MB operand + 33.5 MB output) at 32 envs > 126 MB L2
     xs = [torch.randn(envs, 64, 64, 64, device=dev) for _ in range(nset)]
     film = torch.randn(envs, 128, device=dev) * 0.1
     sts = [ops.gn_stats(x, 32) for x in xs]
+    outs = [torch.empty(envs, 64, 64, 64, device=dev) for _ in range(nset)]
+    ost = [torch.zeros(envs, 2, 2, device=dev, dtype=torch.float64) for _ in range(nset)]
+    opnd = [ops.prep_act(xs[i], mode=1, silu=True, stats0=sts[i], gs0=32, film=film)[0] for i in range(nset)]
     iters = 24
 
     def launch(i):
-        ops.conv2d_fprop(xs[i % nset], wpk, 64, cp, 64, bias=bias, prologue=1, silu=True, stats0=sts[i % nset], gs0=32, film=film, out_gs=32)
+        k = i % nset
+        ops.conv2d_operand(opnd[k], None, 64, 0, envs, 64, 64, wpk, 64, cp, bias=bias, out_gs=32, out=outs[k], ostats=ost[k])
 
-    for i in range(5):
-        launch(i)
-    torch.cuda.synchronize()
-    # the Python wrapper (allocation + ctypes) costs more than the kernel, so the launches are captured in a CUDA graph
-    # and the replay is what is timed (events on the replay stream)
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(iters):
-                launch(i)
+    def launch_prep(i):
+        k = i % nset
+        ops.prep_act(xs[k], mode=1, silu=True, stats0=sts[k], gs0=32, film=film)
+
+    def time_graph(fn):
+        for i in range(5):
+            fn(i)
         torch.cuda.synchronize()
-        graph.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record(side)
-        for _ in range(reps):
+        # Python call overhead exceeds the kernel time, so the launches are captured in a CUDA graph and the replay is
+        # what is timed (events on the replay stream)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(iters):
+                    fn(i)
+            torch.cuda.synchronize()
             graph.replay()
-        e1.record(side)
-    torch.cuda.synchronize()
-    # each captured launch also carries one tiny memset (zeroing the stats buffer the wrapper allocates)
-    ms = e0.elapsed_time(e1) / (iters * reps)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record(side)
+            for _ in range(reps):
+                graph.replay()
+            e1.record(side)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (iters * reps)
+
+    ms = time_graph(launch)
+    ms_prep = time_graph(launch_prep)
     flops = 2.0 * 576 * 64 * 4096 * envs
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64, fused AdaGN+SiLU prologue, bias+stats epilogue",
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
+            "prep_us_per_launch": ms_prep * 1e3,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            # dram__bytes_read+write per launch from profiles/r01_prof_conv_v3_summary.csv (that capture adds the residual read)
-            "traffic": 75.1e6, "algorithmic_bytes": (256 + 256) * 4096.0 * envs,
+            "traffic": None, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
             "us_per_launch": ms * 1e3, "flop_per_launch": flops, "peak_source": peaks_src + " bf16 burst (fp16 and bf16 share the tensor-pipe rate)"}
 
 

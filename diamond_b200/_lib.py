@@ -10,12 +10,18 @@ DMD_MAX_LEVELS = 8
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
 
+class PrepDesc(C.Structure):
+    _fields_ = [
+        ("src0", _vp), ("src1", _vp), ("C0", _i), ("C1", _i), ("B", _i), ("Hs", _i), ("Ws", _i), ("upsample", _i),
+        ("mode", _i), ("silu", _i), ("stats0", _vp), ("stats1", _vp), ("gs0", _i), ("gs1", _i),
+        ("film", _vp), ("film_stride", _i), ("film_off", _i), ("gamma", _vp), ("beta", _vp), ("eps", _f),
+        ("dst0", _vp), ("dst1", _vp), ("dst_raw0", _vp), ("dst_raw1", _vp),
+    ]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
-        ("src0", _vp), ("src1", _vp), ("C0", _i), ("C1", _i), ("Cin", _i), ("B", _i), ("Hs", _i), ("Ws", _i),
-        ("upsample", _i), ("taps", _i), ("stride", _i), ("prologue", _i), ("silu", _i),
-        ("stats0", _vp), ("stats1", _vp), ("gs0", _i), ("gs1", _i),
-        ("film", _vp), ("film_stride", _i), ("film_off", _i), ("gamma", _vp), ("beta", _vp), ("eps", _f),
+        ("src0", _vp), ("src1", _vp), ("C0", _i), ("C1", _i), ("B", _i), ("H", _i), ("W", _i), ("taps", _i), ("stride", _i),
         ("wpk", _vp), ("bias", _vp), ("Cout", _i), ("CoutPad", _i),
         ("residual", _vp), ("out", _vp), ("out_stats", _vp), ("out_gs", _i), ("debug", _i), ("debug_buf", _vp),
     ]
@@ -49,6 +55,8 @@ SIGNATURES = {
     "dmd_last_error": (C.c_char_p, []),
     "dmd_launch_count": (C.c_longlong, [_i]),
     "dmd_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dmd_plc16_bytes": (_sz, [_i, _i, _i, _i]),
+    "dmd_prep_act": (_i, [C.POINTER(PrepDesc), _vp]),
     "dmd_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp]),
     "dmd_gn_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dmd_attn_fwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _vp]),

@@ -58,67 +58,50 @@ static inline int gn_group_size(int C) {  // blocks.py:12,27: num_groups = max(1
 }
 
 // ---------------------------------------------------------------------------------------------- conv launcher
+static size_t plc16_bytes(int B, int H, int W, int C) {
+  const Plc g = plc_geometry(B, H, W);
+  return (size_t)(round_up(C, 16) / 8) * g.Qalloc * 16;
+}
+extern "C" size_t dmd_plc16_bytes(int B, int H, int W, int C) { return plc16_bytes(B, H, W, C); }
+
 static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* tmem_cols) {
   DMD_CHECK(d->src0 && d->out && d->wpk, "conv: null src0/out/wpk");
   DMD_CHECK(d->taps == 9 || d->taps == 1, "conv: taps must be 1 or 9 (got %d)", d->taps);
   DMD_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
-  DMD_CHECK(d->Cin % 16 == 0 && d->Cin >= 16 && d->Cin <= kMaxCin, "conv: Cin=%d must be a multiple of 16 in [16,%d]", d->Cin, kMaxCin);
-  DMD_CHECK(d->C0 % 8 == 0 && d->C1 % 8 == 0 && d->C0 > 0 && d->C0 + d->C1 <= d->Cin, "conv: bad C0=%d C1=%d Cin=%d", d->C0, d->C1, d->Cin);
+  DMD_CHECK(d->C0 > 0 && d->C0 % 16 == 0 && d->C1 % 16 == 0 && d->C0 + d->C1 <= kMaxCin, "conv: operand channels must be multiples of 16, total <= %d (C0=%d C1=%d)", kMaxCin, d->C0, d->C1);
   DMD_CHECK((d->C1 == 0) == (d->src1 == nullptr), "conv: src1/C1 mismatch");
   DMD_CHECK(d->CoutPad % 16 == 0 && d->CoutPad >= 16 && d->CoutPad <= 128 && d->Cout <= d->CoutPad && d->Cout > 0, "conv: bad Cout=%d CoutPad=%d", d->Cout, d->CoutPad);
   memset(p, 0, sizeof(*p));
-  p->src0 = d->src0; p->src1 = d->src1; p->C0 = d->C0; p->C1 = d->C1; p->Cin = d->Cin;
-  p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample ? 1 : 0;
-  p->H = d->upsample ? 2 * d->Hs : d->Hs;
-  p->W = d->upsample ? 2 * d->Ws : d->Ws;
-  p->taps = d->taps; p->stride = d->stride;
+  p->src0 = (const uint8_t*)d->src0; p->src1 = (const uint8_t*)d->src1; p->C0 = d->C0; p->C1 = d->C1; p->Cin = d->C0 + d->C1;
+  p->B = d->B; p->H = d->H; p->W = d->W; p->taps = d->taps; p->stride = d->stride;
   if (d->stride == 2) DMD_CHECK(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H,W");
-  p->pro = d->prologue; p->act = d->silu ? 1 : 0;
-  if (d->prologue) {
-    DMD_CHECK(d->stats0 && d->gs0 > 0 && d->C0 % d->gs0 == 0 && d->gs0 % 8 == 0, "conv: prologue needs stats0/gs0 (gs multiple of 8)");
-    if (d->C1) DMD_CHECK(d->stats1 && d->gs1 > 0 && d->C1 % d->gs1 == 0 && d->gs1 % 8 == 0, "conv: prologue needs stats1/gs1");
-    if (d->prologue == 1) DMD_CHECK(d->film != nullptr, "conv: AdaGN prologue needs film");
-    if (d->prologue == 2) DMD_CHECK(d->gamma && d->beta, "conv: GN prologue needs gamma/beta");
-    DMD_CHECK(d->upsample == 0, "conv: prologue + upsample unsupported");
-    DMD_CHECK(d->C0 / d->gs0 + (d->C1 ? d->C1 / d->gs1 : 0) <= 4, "conv: at most 4 GroupNorm groups over the concatenated input");
-  }
-  p->st0 = d->stats0; p->st1 = d->stats1; p->gs0 = d->gs0 > 0 ? d->gs0 : 8; p->gs1 = d->gs1 > 0 ? d->gs1 : 8;
-  p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off;
-  p->gamma = d->gamma; p->beta = d->beta; p->eps = d->eps;
   p->wpk = reinterpret_cast<const __half*>(d->wpk); p->bias = d->bias; p->Cout = d->Cout; p->CoutPad = d->CoutPad;
   p->resid = d->residual; p->out = d->out; p->ostats = d->out_stats; p->ogs = d->out_gs > 0 ? d->out_gs : d->Cout;
-  if (d->out_stats) DMD_CHECK(d->out_gs > 0 && d->Cout % d->out_gs == 0 && d->out_gs % 16 == 0, "conv: out_gs=%d must divide Cout and be a multiple of 16", d->out_gs);
   p->dbg = d->debug; p->dbg_buf = (long long*)d->debug_buf;
-  p->PW = p->W + 1; p->PH = p->H + 1;
-  const long long Q = (long long)p->B * p->PH * p->PW;
-  DMD_CHECK(Q * (p->PW > p->PH ? p->PW : p->PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
-  p->Q = (int)Q;
-  const int halo = d->taps == 9 ? p->PW + 1 : 0;
+  const Plc g = plc_geometry(d->B, d->H, d->W);
+  p->PW = g.PW; p->PH = g.PH; p->Q = g.Q; p->G = g.G; p->plane_bytes = (unsigned long long)g.Qalloc * 16;
+  DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
+  const int halo = d->taps == 9 ? g.PW + 1 : 0;
   p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
-  p->group_warps = ((2 * p->P + kItemsPerThread - 1) / kItemsPerThread + 31) / 32;
-  if (p->group_warps < 2) p->group_warps = 2;
-  DMD_CHECK(p->group_warps <= kMaxGroupWarps, "conv: W=%d too wide for the linear halo (P=%d); needs the strip path", p->W, p->P);
-  DMD_CHECK((p->P + p->PH * p->PW - 1) / (p->PH * p->PW) + 1 <= kMaxImgSlots, "conv: image too small for tile (H=%d W=%d)", p->H, p->W);
-  if (d->out_stats) DMD_CHECK(p->PH * p->PW >= 64, "conv: image too small for the statistics epilogue (a tile may touch at most %d images)", kStatSlots);
   if (d->out_stats) {
     const int L4 = d->Cout / 4;
+    DMD_CHECK(g.PH * g.PW >= 64, "conv: image too small for the statistics epilogue (a tile may touch at most %d images)", kStatSlots);
     DMD_CHECK(d->Cout % 4 == 0 && (L4 == 4 || L4 == 8 || L4 == 16 || L4 == 32), "conv: out_stats needs Cout in {16,32,64,128} (got %d)", d->Cout);
     DMD_CHECK(d->out_gs == 16 || d->out_gs == 32 || d->out_gs == 64 || d->out_gs == 128, "conv: out_gs must be 16/32/64/128");
-    DMD_CHECK(d->Cout / d->out_gs <= kMaxOutGroups, "conv: too many output groups");
+    DMD_CHECK(d->Cout % d->out_gs == 0 && d->Cout / d->out_gs <= kMaxOutGroups, "conv: bad output groups");
   }
-  p->dPW.init(p->PW); p->dPH.init(p->PH);
-  p->num_tiles = (p->Q + kTileM - 1) / kTileM;
-  // slab ring depth: as many 16-channel slabs as fit next to the resident weights, at most two tiles' worth
+  p->dPW.init(g.PW); p->dPH.init(g.PH);
+  p->num_tiles = (g.Q + kTileM - 1) / kTileM;
+  // slab ring: everything that fits next to the resident weights, at most four tiles' worth
   const int kslabs = p->Cin / 16;
   const ConvSmemLayout L0 = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, 0);
   const long long budget = 227ll * 1024 - (long long)L0.total;
   int stages = (int)(budget / (long long)L0.slab_bytes);
-  if (stages > 2 * kslabs && stages > 6) stages = 2 * kslabs > 6 ? 2 * kslabs : 6;
+  if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
   DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
   p->stages = stages;
-  const ConvSmemLayout L = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, stages);
-  *smem = L.total;
+  *smem = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, stages).total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
   return 0;
 }
@@ -144,11 +127,53 @@ template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
-  const int threads = (kLoadGroups * p.group_warps + 1 + kEpiWarps) * 32;
-  conv_tc_kernel<kCols><<<grid, threads, smem, st>>>(p);
+  conv_tc_kernel<kCols><<<grid, kConvThreads, smem, st>>>(p);
   DMD_LAUNCH_OK();
   return 0;
 }
+
+// ---- prep (GroupNorm / AdaGroupNorm / SiLU / upsample -> PLC16 operand)
+static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
+  DMD_CHECK(d->src0 && d->dst0, "prep: null src0/dst0");
+  DMD_CHECK(d->C0 % 8 == 0 && d->C1 % 8 == 0 && d->C0 > 0 && d->C0 <= kMaxCin && d->C1 <= kMaxCin, "prep: channels must be multiples of 8 (C0=%d C1=%d)", d->C0, d->C1);
+  DMD_CHECK((d->C1 == 0) == (d->src1 == nullptr) && (d->C1 == 0) == (d->dst1 == nullptr), "prep: src1/dst1/C1 mismatch");
+  DMD_CHECK(d->mode >= 0 && d->mode <= 2, "prep: bad mode");
+  memset(p, 0, sizeof(*p));
+  p->s[0].src = d->src0; p->s[0].C = d->C0; p->s[0].Cpad = round_up(d->C0, 16); p->s[0].stats = d->stats0; p->s[0].gs = d->gs0 > 0 ? d->gs0 : 8;
+  p->s[0].c_offset = 0; p->s[0].dst = (uint8_t*)d->dst0; p->s[0].dst_raw = (uint8_t*)d->dst_raw0;
+  p->s[1].src = d->src1; p->s[1].C = d->C1; p->s[1].Cpad = round_up(d->C1 > 0 ? d->C1 : 16, 16); p->s[1].stats = d->stats1; p->s[1].gs = d->gs1 > 0 ? d->gs1 : 8;
+  p->s[1].c_offset = d->C0; p->s[1].dst = (uint8_t*)d->dst1; p->s[1].dst_raw = (uint8_t*)d->dst_raw1;
+  if (d->mode) {
+    DMD_CHECK(d->stats0 && d->gs0 > 0 && d->C0 % d->gs0 == 0, "prep: norm mode needs stats0/gs0");
+    if (d->C1) DMD_CHECK(d->stats1 && d->gs1 > 0 && d->C1 % d->gs1 == 0, "prep: norm mode needs stats1/gs1");
+    if (d->mode == 1) DMD_CHECK(d->film != nullptr, "prep: AdaGroupNorm needs film");
+    if (d->mode == 2) DMD_CHECK(d->gamma && d->beta, "prep: GroupNorm needs gamma/beta");
+    DMD_CHECK(d->upsample == 0, "prep: norm + upsample unsupported");
+  }
+  p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample ? 1 : 0;
+  p->H = d->upsample ? 2 * d->Hs : d->Hs; p->W = d->upsample ? 2 * d->Ws : d->Ws;
+  p->mode = d->mode; p->act = d->silu ? 1 : 0;
+  p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off; p->film_ctot = d->C0 + d->C1;
+  p->gamma = d->gamma; p->beta = d->beta; p->eps = d->eps;
+  const Plc g = plc_geometry(d->B, p->H, p->W);
+  DMD_CHECK(g.PH * g.PW >= kPrepPos, "prep: image too small");
+  DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "prep: problem too large for 32-bit position math");
+  p->PW = g.PW; p->PH = g.PH; p->Q = g.Q; p->G = g.G; p->Qalloc = g.Qalloc; p->plane_bytes = (unsigned long long)g.Qalloc * 16;
+  p->dPW.init(g.PW); p->dPH.init(g.PH);
+  *nsrc = d->C1 ? 2 : 1;
+  return 0;
+}
+static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
+  prep_act_kernel<<<dim3((p.Qalloc + kPrepPos - 1) / kPrepPos, 1, nsrc), kPrepThreads, 0, st>>>(p);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+extern "C" int dmd_prep_act(const dmd_prep_desc* d, void* stream) {
+  PrepParams p; int nsrc;
+  if (prep_fill(d, &p, &nsrc)) return 1;
+  return prep_launch(p, nsrc, (cudaStream_t)stream);
+}
+
 static int conv_launch(const ConvParams& p, size_t smem, int tmem_cols, cudaStream_t st) {
   switch (tmem_cols) {
     case 32: return conv_launch_t<32>(p, smem, st);
@@ -242,8 +267,9 @@ struct ResBlockW {
 
 struct Tens { float* data; double* stats; int C, H, W, gs; };
 
-enum OpKind { OP_CONV = 0, OP_ATTN = 1 };
-struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; };
+enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2 };
+struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; };
+constexpr int kScratchSlots = 8;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
 
 struct Plan {
   int B = 0, H = 0, W = 0;
@@ -253,6 +279,8 @@ struct Plan {
   double* stats = nullptr; size_t stats_bytes = 0;
   int CP_in = 0, CF = 0;
   std::vector<Op> ops;
+  uint8_t* scratch[kScratchSlots] = {nullptr};
+  int scratch_next = 0;
   // sampler state (NCHW fp32)
   float *s_obs = nullptr, *s_x[2] = {nullptr, nullptr}, *s_x2 = nullptr, *s_d = nullptr, *s_traj = nullptr, *s_eps = nullptr;
   int64_t* s_act = nullptr;
@@ -323,7 +351,7 @@ int build_structure(dmd_denoiser* h) {
   h->i_fourier = w.idx++; h->i_actemb = w.idx++;
   h->i_cp0w = w.idx++; h->i_cp0b = w.idx++; h->i_cp2w = w.idx++; h->i_cp2b = w.idx++;
   const int cin_real = (c.num_steps_conditioning + 1) * c.img_channels;
-  const int cin_store = round_up(cin_real, 8);
+  const int cin_store = round_up(cin_real, 16);
   h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0);
   h->d_blocks.resize(L);
   for (int i = 0; i < L; ++i) {
@@ -372,40 +400,65 @@ struct PlanBuilder {
   }
   const float* P(int idx) const { return h->ptrs.empty() ? nullptr : h->ptrs[idx]; }
 
-  void conv(const ConvW& cw, const Tens& a, const Tens* b, int upsample, int stride, int pro, const FilmW* film,
-            int gamma_idx, int beta_idx, bool silu, const Tens* resid, Tens& out, bool out_stats) {
-    dmd_conv_desc d; memset(&d, 0, sizeof(d));
-    d.src0 = a.data; d.C0 = a.C; d.src1 = b ? b->data : nullptr; d.C1 = b ? b->C : 0; d.Cin = cw.Cin;
-    d.B = pl->B; d.Hs = a.H; d.Ws = a.W; d.upsample = upsample; d.taps = cw.taps; d.stride = stride;
-    d.prologue = pro; d.silu = silu;
-    d.stats0 = a.stats; d.gs0 = a.gs; d.stats1 = b ? b->stats : nullptr; d.gs1 = b ? b->gs : 0;
-    if (film) { d.film = pl->film; d.film_stride = h->film_rows; d.film_off = film->off; }
-    if (pro == 2) { d.gamma = P(gamma_idx); d.beta = P(beta_idx); }
+  // PLC16 operands produced by one prep launch
+  struct Operand { uint8_t* n0 = nullptr; uint8_t* n1 = nullptr; uint8_t* r0 = nullptr; uint8_t* r1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0; };
+
+  uint8_t* scratch() {
+    uint8_t* p = pl->scratch[pl->scratch_next];
+    pl->scratch_next = (pl->scratch_next + 1) % kScratchSlots;
+    return p ? p : (uint8_t*)1;
+  }
+
+  // mode 0 raw / 1 AdaGroupNorm(film) / 2 GroupNorm(gamma,beta); also_raw: additionally emit the raw operand (skip projection)
+  Operand prep(const Tens& a, const Tens* b, int upsample, int mode, const FilmW* film, int gamma_idx, int beta_idx, bool silu, bool also_raw) {
+    Operand o;
+    dmd_prep_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = a.data ? a.data : (const float*)1; d.C0 = a.C; d.src1 = b ? (b->data ? b->data : (const float*)1) : nullptr; d.C1 = b ? b->C : 0;
+    d.B = pl->B; d.Hs = a.H; d.Ws = a.W; d.upsample = upsample; d.mode = mode; d.silu = silu;
+    if (mode) {
+      d.stats0 = a.stats ? a.stats : (const double*)1; d.gs0 = a.gs;
+      if (b) { d.stats1 = b->stats ? b->stats : (const double*)1; d.gs1 = b->gs; }
+    }
+    if (mode == 1) { d.film = pl->film ? pl->film : (const float*)1; d.film_stride = h->film_rows; d.film_off = film->off; }
+    if (mode == 2) { d.gamma = P(gamma_idx) ? P(gamma_idx) : (const float*)1; d.beta = P(beta_idx) ? P(beta_idx) : (const float*)1; }
     d.eps = kGnEps;
+    o.n0 = scratch(); d.dst0 = o.n0;
+    if (b) { o.n1 = scratch(); d.dst1 = o.n1; }
+    if (also_raw) { o.r0 = scratch(); d.dst_raw0 = o.r0; if (b) { o.r1 = scratch(); d.dst_raw1 = o.r1; } }
+    o.C0 = round_up(a.C, 16); o.C1 = b ? round_up(b->C, 16) : 0;
+    o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
+    Op op; op.kind = OP_PREP;
+    if (prep_fill(&d, &op.prep, &op.prep_nsrc)) { err = 1; return o; }
+    pl->ops.push_back(op);
+    return o;
+  }
+
+  void conv(const ConvW& cw, const Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats) {
+    dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = raw ? in.r0 : in.n0; d.src1 = in.C1 ? (raw ? in.r1 : in.n1) : nullptr;
+    d.C0 = in.C0; d.C1 = in.C1; d.B = pl->B; d.H = in.H; d.W = in.W; d.taps = cw.taps; d.stride = stride;
     d.wpk = h->packed ? h->packed + cw.pk_off : (const void*)1; d.bias = P(cw.b_idx);
     d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
-    d.residual = resid ? resid->data : nullptr; d.out = out.data ? out.data : (float*)1;
-    d.out_stats = out_stats ? out.stats : nullptr; d.out_gs = out.gs;
-    if (!d.src0) d.src0 = (const float*)1;
-    if (b && !d.src1) d.src1 = (const float*)1;
-    if (pro && !d.stats0) d.stats0 = (const double*)1;
-    if (pro && b && !d.stats1) d.stats1 = (const double*)1;
-    if (pro == 1 && !d.film) d.film = (const float*)1;
-    if (pro == 2 && !d.gamma) { d.gamma = (const float*)1; d.beta = (const float*)1; }
+    d.residual = resid ? (resid->data ? resid->data : (const float*)1) : nullptr; d.out = out.data ? out.data : (float*)1;
+    d.out_stats = out_stats ? (out.stats ? out.stats : (double*)1) : nullptr; d.out_gs = out.gs;
+    if (in.C0 + in.C1 != cw.Cin) { fail("plan: operand channels %d+%d do not match the packed weights (%d)", in.C0, in.C1, cw.Cin); err = 1; return; }
     Op op; op.kind = OP_CONV;
     if (conv_fill(&d, &op.conv, &op.smem, &op.cols)) { err = 1; return; }
     pl->ops.push_back(op);
   }
 
+  // ResBlock.forward (blocks.py:141-147)
   Tens resblock(const ResBlockW& rb, const Tens& x, const Tens* skip) {
     const int H = x.H, W = x.W;
+    Operand in1 = prep(x, skip, 0, 1, &rb.n1, 0, 0, true, rb.has_proj != 0);
     Tens r;
-    if (rb.has_proj) { r = tensor(rb.cout, H, W, false); conv(rb.proj, x, skip, 0, 1, 0, nullptr, 0, 0, false, nullptr, r, false); }
+    if (rb.has_proj) { r = tensor(rb.cout, H, W, false); conv(rb.proj, in1, true, 1, nullptr, r, false); }
     else r = x;
     Tens t = tensor(rb.cout, H, W, true);
-    conv(rb.c1, x, skip, 0, 1, 1, &rb.n1, 0, 0, true, nullptr, t, true);
+    conv(rb.c1, in1, false, 1, nullptr, t, true);
+    Operand in2 = prep(t, nullptr, 0, 1, &rb.n2, 0, 0, true, false);
     Tens o = tensor(rb.cout, H, W, true);
-    conv(rb.c2, t, nullptr, 0, 1, 1, &rb.n2, 0, 0, true, &r, o, true);
+    conv(rb.c2, in2, false, 1, &r, o, true);
     if (!rb.has_attn) return o;
     Tens a = tensor(rb.cout, H, W, true);
     Op op; op.kind = OP_ATTN;
@@ -419,6 +472,12 @@ struct PlanBuilder {
     const int L = c.num_levels, B = pl->B, H = pl->H, W = pl->W;
     const int div = 1 << (L - 1);
     if (H % div || W % div) return fail("denoiser: H=%d W=%d must be multiples of %d (UNet pad path, blocks.py:225-229, not built yet)", H, W, div);
+    // operand scratch pool: sized for the largest operand of the network (level 0, widest channel count)
+    int cmax = 16;
+    for (int i = 0; i < L; ++i) cmax = c.channels[i] > cmax ? c.channels[i] : cmax;
+    const size_t slot_bytes = (plc16_bytes(B, H, W, cmax) + 255) & ~(size_t)255;
+    for (int i = 0; i < kScratchSlots; ++i) pl->scratch[i] = (uint8_t*)bump->take(slot_bytes);
+    pl->scratch_next = 0;
     pl->CP_in = h->conv_in.c0_store;
     pl->xin = (float*)bump->take((size_t)B * H * W * pl->CP_in * 4);
     pl->cs = (float*)bump->take((size_t)(B + 1) * 4 * 4);  // +1: scalar sigma slot used by the sampler
@@ -428,11 +487,14 @@ struct PlanBuilder {
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
     Tens x = tensor(c.channels[0], H, W, true);
-    conv(h->conv_in, xin, nullptr, 0, 1, 0, nullptr, 0, 0, false, nullptr, x, true);
+    conv(h->conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 1, nullptr, x, true);
     std::vector<std::vector<Tens>> d_outputs;
     for (int i = 0; i < L; ++i) {
       Tens xd = x;
-      if (i > 0) { xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true); conv(h->downs[i], x, nullptr, 0, 2, 0, nullptr, 0, 0, false, nullptr, xd, true); }
+      if (i > 0) {  // Downsample (blocks.py:93-100): raw input, stride 2
+        xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true);
+        conv(h->downs[i], prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 2, nullptr, xd, true);
+      }
       std::vector<Tens> outs{xd};
       x = xd;
       for (auto& rb : h->d_blocks[i]) { x = resblock(rb, x, nullptr); outs.push_back(x); }
@@ -441,7 +503,10 @@ struct PlanBuilder {
     for (auto& rb : h->mid) x = resblock(rb, x, nullptr);
     for (int m = 0; m < L; ++m) {
       Tens xu = x;
-      if (m > 0) { xu = tensor(x.C, x.H * 2, x.W * 2, true); conv(h->ups[m], x, nullptr, 1, 1, 0, nullptr, 0, 0, false, nullptr, xu, true); }
+      if (m > 0) {  // Upsample (blocks.py:103-110): nearest x2 folded into the operand, then conv
+        xu = tensor(x.C, x.H * 2, x.W * 2, true);
+        conv(h->ups[m], prep(x, nullptr, 1, 0, nullptr, 0, 0, false, false), false, 1, nullptr, xu, true);
+      }
       x = xu;
       const std::vector<Tens>& skip = d_outputs[L - 1 - m];  // reversed(d_outputs); block k uses skip[::-1][k]
       const int ns = (int)skip.size();
@@ -450,7 +515,8 @@ struct PlanBuilder {
     pl->CF = c.img_channels;
     pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
     Tens f{pl->fout, nullptr, pl->CF, H, W, pl->CF};
-    conv(h->conv_out, x, nullptr, 0, 1, 2, nullptr, h->i_normout_w, h->i_normout_b, true, nullptr, f, false);
+    // conv_out(silu(norm_out(x)))  (inner_model.py:48)
+    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false), false, 1, nullptr, f, false);
     // sampler buffers
     const size_t img = (size_t)B * c.img_channels * H * W * 4;
     pl->s_obs = (float*)bump->take(img * c.num_steps_conditioning);
@@ -498,6 +564,7 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
                     pl.B, c.cond_channels, h->film_rows, 0, st)) return 1;
   for (const Op& op : pl.ops) {
     if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
+    else if (op.kind == OP_PREP) { if (prep_launch(op.prep, op.prep_nsrc, st)) return 1; }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
   return 0;
@@ -750,7 +817,7 @@ ConvW ac_conv(int& idx, size_t& pk, int cout, int cin_real, int taps, int c0_sto
 }
 
 struct AcBuffers {
-  float* x0; std::vector<float*> r, y, pooled; std::vector<double*> st_in, st_y; float *gates, *hx, *cx; double* stats; size_t stats_bytes; size_t total;
+  float* x0; void* opnd; std::vector<float*> r, y, pooled; std::vector<double*> st_in, st_y; float *gates, *hx, *cx; double* stats; size_t stats_bytes; size_t total;
 };
 
 // lays out the workspace; base may be null (size query)
@@ -768,6 +835,7 @@ int ac_layout(const dmd_actor_critic* h, int B, uint8_t* base, AcBuffers* o) {
   o->stats = (double*)base; o->stats_bytes = (sb.off + 255) & ~(size_t)255;
   Bump bb{base ? base + o->stats_bytes : nullptr};
   o->x0 = (float*)bb.take((size_t)B * S * S * h->conv0.c0_store * 4);
+  o->opnd = bb.take(plc16_bytes(B, S, S, 64));  // one operand buffer: every conv's prep immediately precedes it on the stream
   float* cur = (float*)bb.take((size_t)B * S * S * c.channels[0] * 4);  // conv0 output
   o->r.assign(nl, nullptr); o->y.assign(nl, nullptr); o->pooled.assign(nl + 1, nullptr);
   o->pooled[0] = cur;
@@ -796,7 +864,7 @@ extern "C" dmd_actor_critic* dmd_actor_critic_create(const dmd_actor_critic_conf
   int idx = 0; size_t pk = 0;
   // registration order (actor_critic.py:41-47,101-110): encoder.encoder.{0: Conv3x3, k: SmallResBlock(f.0.norm, f.2, skip_projection),
   // MaxPool...}, lstm.{weight_ih, weight_hh, bias_ih, bias_hh}, critic_linear, actor_linear
-  h->conv0 = ac_conv(idx, pk, cfg->channels[0], cfg->img_channels, 9, round_up(cfg->img_channels, 8));
+  h->conv0 = ac_conv(idx, pk, cfg->channels[0], cfg->img_channels, 9, round_up(cfg->img_channels, 16));
   int S = cfg->img_size;
   for (int i = 0; i < cfg->num_levels; ++i) {
     dmd_actor_critic::Level lv;
@@ -848,13 +916,19 @@ extern "C" int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float*
   DMD_CUDA(cudaMemsetAsync(b.stats, 0, b.stats_bytes, st));
   int S = c.img_size;
   if (dmd_nchw_to_nhwc(obs, b.x0, B, c.img_channels, h->conv0.c0_store, S * S, st)) return 1;
+  uint8_t* opnd = (uint8_t*)b.opnd;
   auto run_conv = [&](const ConvW& cw, const float* src, int Csrc, int hw, int pro, int gamma_idx, int beta_idx, const double* st_in,
                       const float* resid, float* out, double* st_out) -> int {
+    dmd_prep_desc pd; memset(&pd, 0, sizeof(pd));
+    pd.src0 = src; pd.C0 = Csrc; pd.B = B; pd.Hs = hw; pd.Ws = hw; pd.mode = pro; pd.silu = pro ? 1 : 0;
+    pd.stats0 = st_in; pd.gs0 = pro ? gn_group_size(Csrc) : 0;
+    if (pro) { pd.gamma = h->ptrs[gamma_idx]; pd.beta = h->ptrs[beta_idx]; }
+    pd.eps = kGnEps; pd.dst0 = opnd;
+    PrepParams pp; int nsrc;
+    if (prep_fill(&pd, &pp, &nsrc) || prep_launch(pp, nsrc, st)) return 1;
     dmd_conv_desc d; memset(&d, 0, sizeof(d));
-    d.src0 = src; d.C0 = Csrc; d.Cin = cw.Cin; d.B = B; d.Hs = hw; d.Ws = hw; d.taps = cw.taps; d.stride = 1;
-    d.prologue = pro; d.silu = pro ? 1 : 0; d.stats0 = st_in; d.gs0 = pro ? gn_group_size(Csrc) : 0;
-    if (pro) { d.gamma = h->ptrs[gamma_idx]; d.beta = h->ptrs[beta_idx]; }
-    d.eps = kGnEps; d.wpk = h->packed + cw.pk_off; d.bias = h->ptrs[cw.b_idx]; d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
+    d.src0 = opnd; d.C0 = round_up(Csrc, 16); d.B = B; d.H = hw; d.W = hw; d.taps = cw.taps; d.stride = 1;
+    d.wpk = h->packed + cw.pk_off; d.bias = h->ptrs[cw.b_idx]; d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
     d.residual = resid; d.out = out; d.out_stats = st_out; d.out_gs = gn_group_size(cw.Cout);
     ConvParams p; size_t smem; int cols;
     if (conv_fill(&d, &p, &smem, &cols)) return 1;

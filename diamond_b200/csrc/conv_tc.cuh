@@ -1,47 +1,39 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC fp32 activations.  Persistent + warp-specialised.
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).  Persistent, warp-specialised, TMA-fed.
 //
 // Replaces, on the hot path, every nn.Conv2d of the reference (blocks.py:18-19 Conv1x1/Conv3x3, :96 Downsample,
-// :109-110 Upsample, inner_model.py:36,41 conv_in/conv_out) together with what the reference runs around it:
-//   prologue : GroupNorm / AdaGroupNorm apply (blocks.py:28,43-45) + SiLU (blocks.py:143-144) on the conv INPUT,
-//              channel concat of the skip tensor (blocks.py:174), nearest-2x upsample (blocks.py:109)
-//   epilogue : bias, residual add (blocks.py:145), stride-2 subsample (blocks.py:96), and the (sum, sumsq) partials of
-//              the NEXT GroupNorm over the conv OUTPUT.
+// :109-110 Upsample conv, inner_model.py:36,41 conv_in/conv_out) plus its epilogue neighbours: bias, residual add
+// (blocks.py:145), stride-2 subsample (blocks.py:96) and the (sum, sumsq) partials of the NEXT GroupNorm.
+// What the reference applies to the conv INPUT (GroupNorm / AdaGroupNorm + SiLU, concat, nearest-2x upsample) is done once
+// per element by prep_act_kernel (below), which writes the activation operand in the layout this kernel consumes.
 //
-// Geometry ("padded-linear" implicit GEMM).  Pixels of all B images are laid out on one line with pitch
+// Operand layout "PLC16" (padded-linear, chunk-major, fp16).  Pixels of all B images lie on one line with pitch
 // PW = W+1 and PH = H+1 rows per image: q = (n*PH + y)*PW + x.  Column x==W and row y==H are zero padding shared
-// between neighbouring rows / images, so tap (dy,dx) of a 3x3 window is simply position q + dy*PW + dx.
-// A tile is 128 consecutive q (the MMA M dimension).  Its normalised fp16 halo [q0-PW-1, q0+128+PW+1) is staged ONCE
-// in shared memory in the UMMA no-swizzle K-major layout, one "slab" per 16 input channels:
-//     slab = [2 chunks of 8 channels][P positions][16 B]          (LBO = Palloc*16, SBO = 128)
+// between neighbouring rows / images, so tap (dy,dx) of a 3x3 window is simply position q + dy*PW + dx.  The tensor is
+// stored as one plane per 8-channel chunk:   plane[j][G + q] = 8 fp16 channels = 16 bytes   (G = PW+1 zero guard
+// positions in front, PW+1 behind the last tile).  A 128-row tile needs, per 16 input channels ("slab"), positions
+// [q0-PW-1, q0+128+PW+1) of two planes: two CONTIGUOUS byte ranges.  One thread fetches them with cp.async.bulk straight
+// into the UMMA no-swizzle K-major shared-memory layout  [2 chunks][P positions][16 B]  (LBO = Palloc*16, SBO = 128),
 // and every tap reads the same slab through a descriptor whose start address is shifted by (dy*PW+dx)*16 B.
 //
-// Roles (one CTA per SM, each CTA owns a contiguous range of tiles):
-//   3 loader groups (WG warps each): group j produces slabs g = j, j+3, ... of the CTA's slab sequence, so three slabs are
-//       in flight and global-load latency is hidden ACROSS groups.  (It cannot be hidden inside a thread: the
-//       generic->async proxy fence a writer must execute before the MMA may read its slab is a MEMBAR that also drains
-//       that thread's outstanding loads.)  Per slab a thread issues the loads of its 3 (position, 8-channel) items,
-//       computes the slab's GroupNorm/FiLM coefficients while they fly, applies affine + SiLU, converts to fp16, stores.
-//   1 MMA warp  : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap) from precomputed descriptor
-//       words; tcgen05.commit frees the slab and, after the last slab of a tile, publishes the TMEM accumulator.
-//   8 epilogue warps: TMEM -> registers (+bias) -> shared staging (transpose) -> coalesced 16-byte global stores with the
-//       residual added on the way and GroupNorm (sum, sumsq) partials reduced per tile.
+// Roles (320 threads, one CTA per SM, contiguous balanced tile ranges):
+//   warp 0      producer: mbarrier expect_tx + 2 bulk copies per slab into a deep ring (empty/full mbarriers)
+//   warp 1      MMA     : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap) from precomputed
+//                         descriptor words; tcgen05.commit frees the slab / publishes the TMEM accumulator
+//   warps 2-9   epilogue: TMEM -> registers (+bias) -> shared staging (transpose) -> coalesced 16-byte global stores with
+//                         the residual added on the way; per-tile deterministic GroupNorm partial sums -> fp64 atomics
 // Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
-// TMEM holds two accumulators so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// TMEM holds two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "ptx.cuh"
 
 namespace dmd {
 
-constexpr int kLoadGroups = 3;
-constexpr int kItemsPerThread = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kMaxGroupWarps = 6;
-constexpr int kMaxConvThreads = (kLoadGroups * kMaxGroupWarps + 1 + kEpiWarps) * 32;  // 864
+constexpr int kConvThreads = (2 + kEpiWarps) * 32;  // 320
 constexpr int kTileM = 128;
-constexpr int kMaxImgSlots = 4;
 constexpr int kMaxCin = 128;
-constexpr int kMaxStages = 16;
+constexpr int kMaxStages = 24;
 constexpr int kStatSlots = 3;   // images a 128-row tile can touch
 constexpr int kMaxOutGroups = 4;
 
@@ -55,56 +47,50 @@ struct FastDiv {
   __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, m); }
 };
 
+// geometry of a PLC16 tensor over B images of H x W
+struct Plc {
+  int PW, PH, Q, G, Qalloc;
+};
+__host__ __device__ inline Plc plc_geometry(int B, int H, int W) {
+  Plc g;
+  g.PW = W + 1; g.PH = H + 1; g.Q = B * g.PH * g.PW; g.G = g.PW + 1;
+  g.Qalloc = g.G + ((g.Q + kTileM - 1) / kTileM) * kTileM + g.PW + 1;
+  return g;
+}
+
 struct ConvParams {
-  // sources (NHWC fp32).  channel index space of the conv input = [src0 channels | src1 channels | zero pad]
-  const float* src0;
-  const float* src1;
-  int C0, C1;    // stored channels (multiples of 8); C1 == 0 -> single source
-  int Cin;       // K extent per tap: C0+C1 rounded up to a multiple of 16
-  int B, Hs, Ws; // source spatial size
-  int ups;       // 1: conv input is the nearest-2x upsample of the source (H = 2*Hs)
-  int H, W;      // conv input size
-  int taps;      // 9 (3x3, pad 1) or 1 (1x1)
-  int stride;    // 1 or 2 (stride 2 == stride-1 result sampled at even (y,x); exact for k=3,p=1)
-  // prologue
-  int pro;       // 0: none   1: AdaGroupNorm (FiLM)   2: affine GroupNorm
-  int act;       // 1: SiLU after the prologue affine
-  const double* st0;  // [B][C0/gs0][2] (sum, sumsq) of src0
-  const double* st1;  // [B][C1/gs1][2]
-  int gs0, gs1;
-  const float* film;  // [B][film_stride]; scale at film_off + c, shift at film_off + (C0+C1) + c
-  int film_stride, film_off;
-  const float* gamma; // affine GN weight [C0+C1]
-  const float* beta;
-  float eps;
-  // weights
-  const __half* wpk;  // [taps][Cin/8][CoutPad][8]
-  const float* bias;  // [Cout] or null
+  const uint8_t* src0;  // PLC16 planes of the first source
+  const uint8_t* src1;  // second source (channel concat, blocks.py:174) or null
+  int C0, C1;           // channels per source (multiples of 16)
+  int Cin;              // C0 + C1
+  int B, H, W;          // conv input size
+  int taps;             // 9 (3x3, pad 1) or 1 (1x1)
+  int stride;           // 1 or 2 (stride 2 == stride-1 result sampled at even (y,x); exact for k=3,p=1)
+  const __half* wpk;    // [taps][Cin/8][CoutPad][8]
+  const float* bias;    // [Cout] or null
   int Cout, CoutPad;
-  // epilogue
-  const float* resid; // NHWC [B][Ho][Wo][Cout] or null
-  float* out;         // NHWC [B][Ho][Wo][Cout]
-  double* ostats;     // [B][Cout/ogs][2] accumulated with atomics (caller zeroes) or null
+  const float* resid;   // NHWC [B][Ho][Wo][Cout] or null
+  float* out;           // NHWC [B][Ho][Wo][Cout]
+  double* ostats;       // [B][Cout/ogs][2] accumulated with atomics (caller zeroes) or null
   int ogs;
   // derived (host fills)
-  int PW, PH, Q;      // pitch, rows per image, total positions B*PH*PW
-  int P, Palloc;      // halo positions, odd allocation pitch
+  int PW, PH, Q, G;
+  unsigned long long plane_bytes;  // bytes of one chunk plane (same geometry for both sources)
+  int P, Palloc;        // halo positions, odd allocation pitch
   int num_tiles, stages;
-  int group_warps;    // WG: warps per loader group (ceil(2P / 3 / 32))
   FastDiv dPW, dPH;
   int dbg;
-  long long* dbg_buf;  // bring-up: clock64 timeline of CTA 0, [role 3][tile 16][event 16]
+  long long* dbg_buf;   // bring-up: clock64 timeline of CTA 0, [role 3][tile 16][event 16]
 };
 
 struct ConvSmemLayout {
-  uint32_t ctab_off, bias_off, rowinfo_off, sstat_off, stage_off, w_off, a_off, slab_bytes, stage_pitch, total;
+  uint32_t bias_off, rowinfo_off, sstat_off, stage_off, w_off, a_off, slab_bytes, stage_pitch, total;
 };
 
-// barriers live in the first 512 bytes: wbar, full[16], empty[16], tfull[2], tempty[2], tmem slot
+// barriers live in the first 512 bytes: wbar, full[24], empty[24], tfull[2], tempty[2], tmem slot
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
-  L.ctab_off = 512;  // per group: [a|b][slot 4][kMaxCin] floats + [slot 4][4 groups][mean, rstd]
-  L.bias_off = L.ctab_off + kLoadGroups * (2 * kMaxImgSlots * kMaxCin + kMaxImgSlots * 4 * 2) * 4;
+  L.bias_off = 512;
   L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
   L.sstat_off = L.rowinfo_off + kTileM * 8;          // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
@@ -125,7 +111,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   do { if (p.dbg_buf && blockIdx.x == 0 && (it_) < 16) p.dbg_buf[((role) * 16 + (it_)) * 16 + (ev)] = clock64(); } while (0)
 
 template <int kAccCols>  // TMEM columns per accumulator (>= CoutPad); two accumulators are allocated
-__global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* full = wbar + 1;                 // [kMaxStages]
@@ -134,7 +120,6 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
   uint64_t* tempty = tfull + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc, p.stages);
-  float* ctab = reinterpret_cast<float*>(smem + L.ctab_off);
   float* sbias = reinterpret_cast<float*>(smem + L.bias_off);
   int2* rowinfo = reinterpret_cast<int2*>(smem + L.rowinfo_off);
   float* sstat = reinterpret_cast<float*>(smem + L.sstat_off);
@@ -144,15 +129,10 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int WG = p.group_warps;
-  const int GT = WG * 32;
-  const int mma_warp = kLoadGroups * WG;
-  const int epi_warp0 = mma_warp + 1;
   const int halo = (p.taps == 9) ? (p.PW + 1) : 0;
-  const int Ctot = p.C0 + p.C1;
   const int S = p.stages;
   const int kslabs = p.Cin >> 4;
-  // contiguous, balanced tile range per CTA: neighbouring tiles share halo rows (L1/L2 hits)
+  // contiguous, balanced tile range per CTA: neighbouring tiles share halo rows (L2 hits)
   const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
   const int my_tiles = tiles_lo + ((int)blockIdx.x < tiles_rem ? 1 : 0);
@@ -160,7 +140,7 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
   // ---- setup
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, WG); mbar_init(empty + s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
@@ -168,7 +148,7 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
     for (int t = 0; t < p.taps; ++t)
       bulk_g2s(sW + (size_t)t * tap_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)t * tap_bytes, tap_bytes, wbar);
   }
-  if (warp == mma_warp) tmem_alloc<2 * kAccCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_slot);
   for (int i = tid; i < 128; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
   for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before_sync();
@@ -176,151 +156,34 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < mma_warp) {
-    // =========================================================================================== LOADER GROUPS
-    const int grp = warp / WG;
-    const int gt = tid - grp * GT;  // thread index inside the group
-    const int total = my_tiles * kslabs;
-    float* tA = ctab + (size_t)grp * (2 * kMaxImgSlots * kMaxCin + kMaxImgSlots * 4 * 2);  // a[slot][kMaxCin]
-    float* tB = tA + kMaxImgSlots * kMaxCin;                                                // b[slot][kMaxCin]
-    float* tMR = tB + kMaxImgSlots * kMaxCin;                                               // (mean, rstd)[slot][4]
-    int cur_it = -1, n_first = 0;
-    int pix[kItemsPerThread];
-    uint32_t meta = 0;       // per item: bit (8j) = valid pixel, bits (8j+1..8j+2) = image slot
-    int stage = grp % S;     // ring position of this group's first slab
-    uint32_t phase = (uint32_t)(grp / S) & 1u;
-    int it = 0, ks = grp;
-    while (ks >= kslabs) { ks -= kslabs; ++it; }
-    for (int g = grp; g < total; g += kLoadGroups) {
-      const bool new_tile = (it != cur_it);
-      if (new_tile) {  // decode this thread's items for the new tile
-        cur_it = it;
-        const int qh0 = (tile_begin + it) * kTileM - halo;
-        n_first = (qh0 > 0) ? (int)(p.dPH.div(p.dPW.div((uint32_t)qh0))) : 0;
-        meta = 0;
+  if (warp == 0) {
+    // =========================================================================================== PRODUCER (TMA)
+    if (lane == 0) {
+      const uint32_t chunk_bytes = (uint32_t)p.P * 16;
+      const int NA = p.C0 >> 3;  // chunk planes of the first source
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        // first halo position of this tile inside a plane (guard G keeps it non-negative)
+        const size_t pos0 = (size_t)((tile_begin + it) * kTileM - halo + p.G) * 16;
+        for (int ks = 0; ks < kslabs; ++ks) {
+          DMD_TS(0, it, ks * 3 + 0);
+          mbar_wait(empty + stage, phase ^ 1u);
+          DMD_TS(0, it, ks * 3 + 1);
+          uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
+          mbar_expect_tx(full + stage, 2 * chunk_bytes);
 #pragma unroll
-        for (int j = 0; j < kItemsPerThread; ++j) {
-          pix[j] = 0;
-          const int pp = (gt + j * GT) >> 1;
-          const int q = qh0 + pp;
-          if (pp < p.P && q >= 0 && q < p.Q) {
-            const uint32_t R = p.dPW.div((uint32_t)q);
-            const int x = q - (int)R * p.PW;
-            const uint32_t n = p.dPH.div(R);
-            const int y = (int)R - (int)n * p.PH;
-            if (x < p.W && y < p.H) {
-              const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-              pix[j] = ((int)n * p.Hs + ys) * p.Ws + xs;
-              meta |= (1u | ((uint32_t)((int)n - n_first) << 1)) << (8 * j);
-            }
+          for (int sub = 0; sub < 2; ++sub) {
+            const int j = 2 * ks + sub;
+            const uint8_t* plane = (j < NA) ? p.src0 + (size_t)j * p.plane_bytes : p.src1 + (size_t)(j - NA) * p.plane_bytes;
+            bulk_g2s(slab + (size_t)sub * p.Palloc * 16, plane + pos0, chunk_bytes, full + stage);
           }
+          DMD_TS(0, it, ks * 3 + 2);
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
       }
-      // ---- issue all loads of this slab
-      float4 v0[kItemsPerThread], v1[kItemsPerThread];
-#pragma unroll
-      for (int j = 0; j < kItemsPerThread; ++j) {
-        const int sub = (gt + j * GT) & 1;
-        const int cbase = ks * 16 + sub * 8;
-        v0[j] = make_float4(0.f, 0.f, 0.f, 0.f); v1[j] = v0[j];
-        if (((meta >> (8 * j)) & 1u) && cbase < Ctot && !(p.dbg & 4)) {
-          const float* src; int Csrc, coff;
-          if (cbase < p.C0) { src = p.src0; Csrc = p.C0; coff = cbase; }
-          else { src = p.src1; Csrc = p.C1; coff = cbase - p.C0; }
-          const float4* gp = reinterpret_cast<const float4*>(src + (size_t)pix[j] * Csrc + coff);
-          v0[j] = __ldg(gp); v1[j] = __ldg(gp + 1);
-        }
-      }
-      // ---- new tile: rebuild this group's GroupNorm/FiLM table (all channels, <= 4 images) while the loads fly.
-      //      fp64 only for the <= 16 (image, group) statistics; the per-channel part is fp32.
-      if (new_tile && p.pro != 0) {
-        named_bar_sync(1 + grp, GT);  // everyone in the group is done reading the previous tile's table
-        const int G0 = p.C0 / p.gs0, G1 = p.C1 ? p.C1 / p.gs1 : 0;
-        if (gt < kMaxImgSlots * 4) {
-          const int slot = gt >> 2, gi = gt & 3;
-          const int n = n_first + slot;
-          float mean_f = 0.f, rstd_f = 0.f;
-          if (n < p.B && gi < G0 + G1) {
-            const bool first = gi < G0;
-            const double* st = first ? p.st0 + ((size_t)n * G0 + gi) * 2 : p.st1 + ((size_t)n * G1 + (gi - G0)) * 2;
-            const double cnt = (double)p.Hs * p.Ws * (first ? p.gs0 : p.gs1);
-            const double mean = st[0] / cnt;
-            double var = st[1] / cnt - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            mean_f = (float)mean;
-            rstd_f = (float)(1.0 / sqrt(var + (double)p.eps));
-          }
-          tMR[gt * 2] = mean_f;
-          tMR[gt * 2 + 1] = rstd_f;
-        }
-        named_bar_sync(1 + grp, GT);
-        for (int e = gt; e < kMaxImgSlots * Ctot; e += GT) {
-          const int slot = e / Ctot, c = e - slot * Ctot;
-          const int n = n_first + slot;
-          float a = 0.f, bb = 0.f;
-          if (n < p.B) {
-            const int gi = (c < p.C0) ? c / p.gs0 : G0 + (c - p.C0) / p.gs1;
-            const float mean = tMR[(slot * 4 + gi) * 2], rstd = tMR[(slot * 4 + gi) * 2 + 1];
-            float sc, sh;
-            if (p.pro == 1) {
-              const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
-              sc = 1.f + __ldg(f + c);
-              sh = __ldg(f + Ctot + c);
-            } else {
-              sc = __ldg(p.gamma + c);
-              sh = __ldg(p.beta + c);
-            }
-            a = rstd * sc;
-            bb = sh - mean * a;
-          }
-          tA[slot * kMaxCin + c] = a;
-          tB[slot * kMaxCin + c] = bb;
-        }
-        named_bar_sync(1 + grp, GT);
-      }
-      // ---- wait for the ring slot, transform, store
-      if (gt == 0) DMD_TS(0, it, ks * 3 + 0);
-      mbar_wait(empty + stage, phase ^ 1u);
-      if (gt == 0) DMD_TS(0, it, ks * 3 + 1);
-      uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
-#pragma unroll
-      for (int j = 0; j < kItemsPerThread; ++j) {
-        const int item = gt + j * GT;
-        const int pp = item >> 1, sub = item & 1;
-        if (pp < p.P) {
-          uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-          const uint32_t m = meta >> (8 * j);
-          if ((m & 1u) && (ks * 16 + sub * 8) < Ctot) {
-            float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
-            if (p.pro != 0) {
-              const int slot = (int)((m >> 1) & 3u);
-              const float4* ca = reinterpret_cast<const float4*>(tA + slot * kMaxCin + ks * 16 + sub * 8);
-              const float4* cb = reinterpret_cast<const float4*>(tB + slot * kMaxCin + ks * 16 + sub * 8);
-              const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
-              v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
-              v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
-            }
-            if (p.act && !(p.dbg & 16)) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-            }
-            packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]);
-            packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
-          }
-          *reinterpret_cast<uint4*>(slab + (size_t)sub * p.Palloc * 16 + (size_t)pp * 16) = packed;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full + stage);
-      if (gt == 0) DMD_TS(0, it, ks * 3 + 2);
-      // advance by kLoadGroups slabs
-      ks += kLoadGroups;
-      while (ks >= kslabs) { ks -= kslabs; ++it; }
-      stage += kLoadGroups;
-      while (stage >= S) { stage -= S; phase ^= 1u; }
     }
-  } else if (warp == mma_warp) {
+    __syncwarp();
+  } else if (warp == 1) {
     // =========================================================================================== MMA ISSUER
     // One thread.  Descriptor words are precomputed: per MMA only the 14-bit start-address fields change
     // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
@@ -383,7 +246,7 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
     __syncwarp();
   } else {
     // =========================================================================================== EPILOGUE (8 warps)
-    const int et = tid - epi_warp0 * 32;       // 0..255
+    const int et = tid - 64;                   // 0..255
     const int ew = et >> 5;                    // 0..7
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int first_of_quarter = (ew < 4) ? 1 : 0;   // epilogue warps ew and ew+4 share (warp & 3): they split the columns
@@ -522,7 +385,117 @@ __global__ void __launch_bounds__(kMaxConvThreads, 1) conv_tc_kernel(const ConvP
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == mma_warp) tmem_free<2 * kAccCols>(tmem_base);
+  if (warp == 1) tmem_free<2 * kAccCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prep_act_kernel: one pass over an NHWC fp32 tensor that applies what the reference runs on a conv INPUT and writes the
+// PLC16 operand:  y = act(a[n][c] * x + b[n][c])  with (a, b) from GroupNorm statistics and FiLM (AdaGroupNorm,
+// blocks.py:41-45) or affine weights (blocks.py:28); SiLU (blocks.py:143-144); nearest-2x upsample (blocks.py:109).
+// Guard and padding positions are written as zeros, so the buffer needs no memset.
+// gridDim.z selects the source (a channel concat is two sources with their own statistics but ONE FiLM vector).
+struct PrepSrc {
+  const float* src;    // NHWC [B][Hs][Ws][C]
+  int C;               // channels stored in src (multiple of 8)
+  int Cpad;            // channels of the operand (multiple of 16, >= C; the rest is zero)
+  const double* stats; // [B][C/gs][2] or null (mode 0)
+  int gs;
+  int c_offset;        // channel offset inside the concatenated norm input (FiLM / gamma index = c_offset + c)
+  uint8_t* dst;        // PLC16 planes, normalised/activated
+  uint8_t* dst_raw;    // optional second output: the raw tensor in PLC16 (for the 1x1 skip projection), or null
+};
+struct PrepParams {
+  PrepSrc s[2];
+  int B, Hs, Ws, ups, H, W;
+  int mode;            // 0 raw, 1 AdaGroupNorm, 2 affine GroupNorm
+  int act;             // SiLU
+  const float* film;   // [B][film_stride]; scale at film_off + c, shift at film_off + film_ctot + c
+  int film_stride, film_off, film_ctot;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int PW, PH, Q, G, Qalloc;
+  unsigned long long plane_bytes;
+  FastDiv dPW, dPH;
+};
+
+constexpr int kPrepThreads = 256;
+constexpr int kPrepPos = 32;  // positions per block
+
+__global__ void __launch_bounds__(kPrepThreads) prep_act_kernel(const PrepParams p) {
+  __shared__ float sa[2][kMaxCin], sb[2][kMaxCin];  // coefficients for the (at most 2) images this block touches
+  const PrepSrc& S = p.s[blockIdx.z];
+  const int nch = S.Cpad >> 3;
+  const int pa0 = blockIdx.x * kPrepPos;            // first allocation position of this block
+  const int q_first = pa0 - p.G;
+  const int n0 = q_first > 0 ? (int)p.dPH.div(p.dPW.div((uint32_t)min(q_first, p.Q - 1))) : 0;
+  if (p.mode != 0) {
+    for (int e = threadIdx.x; e < 2 * S.C; e += kPrepThreads) {
+      const int slot = e / S.C, c = e - slot * S.C;
+      const int n = n0 + slot;
+      float a = 0.f, b = 0.f;
+      if (n < p.B) {
+        const int G = S.C / S.gs;
+        const double* st = S.stats + ((size_t)n * G + c / S.gs) * 2;
+        const double cnt = (double)p.Hs * p.Ws * S.gs;
+        const double mean = st[0] / cnt;
+        double var = st[1] / cnt - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+        const int cg = S.c_offset + c;
+        float sc, sh;
+        if (p.mode == 1) {
+          const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
+          sc = 1.f + __ldg(f + cg);
+          sh = __ldg(f + p.film_ctot + cg);
+        } else {
+          sc = __ldg(p.gamma + cg);
+          sh = __ldg(p.beta + cg);
+        }
+        a = rstd * sc;
+        b = sh - (float)mean * a;
+      }
+      sa[slot][c] = a;
+      sb[slot][c] = b;
+    }
+    __syncthreads();
+  }
+  // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row)
+  for (int i = threadIdx.x; i < kPrepPos * nch; i += kPrepThreads) {
+    const int pl = i / nch, j = i - pl * nch;
+    const int pa = pa0 + pl;
+    if (pa >= p.Qalloc) continue;
+    const int q = pa - p.G;
+    uint4 packed = make_uint4(0u, 0u, 0u, 0u), raw = packed;
+    if (q >= 0 && q < p.Q && j * 8 < S.C) {
+      const uint32_t R = p.dPW.div((uint32_t)q);
+      const int x = q - (int)R * p.PW;
+      const uint32_t n = p.dPH.div(R);
+      const int y = (int)R - (int)n * p.PH;
+      if (x < p.W && y < p.H) {
+        const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
+        const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
+        const float4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (S.dst_raw != nullptr) {
+          raw.x = pack_h2(v[0], v[1]); raw.y = pack_h2(v[2], v[3]); raw.z = pack_h2(v[4], v[5]); raw.w = pack_h2(v[6], v[7]);
+        }
+        if (p.mode != 0) {
+          const int slot = (int)n - n0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(sa[slot][j * 8 + k], v[k], sb[slot][j * 8 + k]);
+        }
+        if (p.act) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
+        }
+        packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]); packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+      }
+    }
+    const size_t off = (size_t)j * p.plane_bytes + (size_t)pa * 16;
+    *reinterpret_cast<uint4*>(S.dst + off) = packed;
+    if (S.dst_raw != nullptr) *reinterpret_cast<uint4*>(S.dst_raw + off) = raw;
+  }
 }
 
 }  // namespace dmd

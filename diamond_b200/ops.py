@@ -59,31 +59,68 @@ def gn_stats(x: Tensor, gs: int) -> Tensor:
     return st
 
 
+def prep_act(src0: Tensor, *, src1: Optional[Tensor] = None, upsample: bool = False, mode: int = 0, silu: bool = False,
+             stats0: Optional[Tensor] = None, stats1: Optional[Tensor] = None, gs0: int = 0, gs1: int = 0,
+             film: Optional[Tensor] = None, film_off: int = 0, gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None,
+             eps: float = 1e-5, also_raw: bool = False):
+    """NHWC fp32 -> PLC16 fp16 operand(s) with the conv-input transform fused.  Returns (n0, n1, r0, r1, H, W)."""
+    _cuda(src0, src1, stats0, stats1, film, gamma, beta)
+    lib = _lib.lib()
+    b, hs, ws, c0 = src0.shape
+    h, w = (2 * hs, 2 * ws) if upsample else (hs, ws)
+    c1 = src1.shape[3] if src1 is not None else 0
+
+    def buf(c):
+        return torch.empty(lib.dmd_plc16_bytes(b, h, w, c), dtype=torch.uint8, device=src0.device)
+
+    n0, n1 = buf(c0), (buf(c1) if c1 else None)
+    r0, r1 = (buf(c0) if also_raw else None), (buf(c1) if (also_raw and c1) else None)
+    d = _lib.PrepDesc()
+    d.src0, d.src1, d.C0, d.C1 = src0.data_ptr(), _lib.ptr(src1), c0, c1
+    d.B, d.Hs, d.Ws, d.upsample, d.mode, d.silu = b, hs, ws, int(upsample), mode, int(silu)
+    d.stats0, d.stats1, d.gs0, d.gs1 = _lib.ptr(stats0), _lib.ptr(stats1), gs0, gs1
+    d.film, d.film_stride, d.film_off = _lib.ptr(film), (film.shape[1] if film is not None else 0), film_off
+    d.gamma, d.beta, d.eps = _lib.ptr(gamma), _lib.ptr(beta), eps
+    d.dst0, d.dst1, d.dst_raw0, d.dst_raw1 = n0.data_ptr(), _lib.ptr(n1), _lib.ptr(r0), _lib.ptr(r1)
+    _lib.check(lib.dmd_prep_act(C.byref(d), _lib.current_stream()))
+    return n0, n1, r0, r1, h, w
+
+
+def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h: int, w: int, wpk: Tensor, cout: int,
+                   cout_pad: int, taps: int = 9, *, bias: Optional[Tensor] = None, stride: int = 1,
+                   residual: Optional[Tensor] = None, out_gs: int = 0, out: Optional[Tensor] = None,
+                   ostats: Optional[Tensor] = None, debug: int = 0, debug_buf: Optional[Tensor] = None):
+    """tcgen05 conv on already prepared PLC16 operand(s) (one kernel launch)."""
+    _cuda(n0, n1, wpk, bias, residual)
+    ho, wo = h // stride, w // stride
+    if out is None:
+        out = torch.empty(b, ho, wo, cout, device=n0.device, dtype=torch.float32)
+    if ostats is None and out_gs:
+        ostats = torch.zeros(b, cout // out_gs, 2, device=n0.device, dtype=torch.float64)
+    d = _lib.ConvDesc()
+    d.src0, d.src1, d.C0, d.C1 = n0.data_ptr(), _lib.ptr(n1), c0, c1
+    d.B, d.H, d.W, d.taps, d.stride = b, h, w, taps, stride
+    d.wpk, d.bias, d.Cout, d.CoutPad = wpk.data_ptr(), _lib.ptr(bias), cout, cout_pad
+    d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
+    d.debug_buf = _lib.ptr(debug_buf)
+    _lib.check(_lib.lib().dmd_conv2d_fprop(C.byref(d), _lib.current_stream()))
+    return out, ostats
+
+
 def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: int, taps: int = 9, *,
                  src1: Optional[Tensor] = None, bias: Optional[Tensor] = None, upsample: bool = False, stride: int = 1,
                  prologue: int = 0, silu: bool = False, stats0: Optional[Tensor] = None, stats1: Optional[Tensor] = None,
                  gs0: int = 0, gs1: int = 0, film: Optional[Tensor] = None, film_off: int = 0,
                  gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
                  residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0, debug_buf: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
-    _cuda(src0, src1, wpk, bias, stats0, stats1, film, gamma, beta, residual)
-    b, hs, ws, c0 = src0.shape
-    h, w = (2 * hs, 2 * ws) if upsample else (hs, ws)
-    ho, wo = h // stride, w // stride
-    out = torch.empty(b, ho, wo, cout, device=src0.device, dtype=torch.float32)
-    ostats = torch.zeros(b, cout // out_gs, 2, device=src0.device, dtype=torch.float64) if out_gs else None
-    d = _lib.ConvDesc()
-    d.src0, d.src1 = src0.data_ptr(), _lib.ptr(src1)
-    d.C0, d.C1, d.Cin = c0, (src1.shape[3] if src1 is not None else 0), cin_pad
-    d.B, d.Hs, d.Ws = b, hs, ws
-    d.upsample, d.taps, d.stride, d.prologue, d.silu = int(upsample), taps, stride, prologue, int(silu)
-    d.stats0, d.stats1, d.gs0, d.gs1 = _lib.ptr(stats0), _lib.ptr(stats1), gs0, gs1
-    d.film, d.film_stride, d.film_off = _lib.ptr(film), (film.shape[1] if film is not None else 0), film_off
-    d.gamma, d.beta, d.eps = _lib.ptr(gamma), _lib.ptr(beta), eps
-    d.wpk, d.bias, d.Cout, d.CoutPad = wpk.data_ptr(), _lib.ptr(bias), cout, cout_pad
-    d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
-    d.debug_buf = _lib.ptr(debug_buf)
-    _lib.check(_lib.lib().dmd_conv2d_fprop(C.byref(d), _lib.current_stream()))
-    return out, ostats
+    """The reference's `conv(act(norm(cat(x, skip))))` on NHWC fp32 tensors: one prep launch + one tcgen05 conv launch."""
+    n0, n1, _, _, h, w = prep_act(src0, src1=src1, upsample=upsample, mode=prologue, silu=silu, stats0=stats0, stats1=stats1,
+                                  gs0=gs0, gs1=gs1, film=film, film_off=film_off, gamma=gamma, beta=beta, eps=eps)
+    c0, c1 = round_up(src0.shape[3], 16), (round_up(src1.shape[3], 16) if src1 is not None else 0)
+    if c0 + c1 != cin_pad:
+        raise ValueError(f"operand channels {c0}+{c1} do not match the packed weights ({cin_pad})")
+    return conv2d_operand(n0, n1, c0, c1, src0.shape[0], h, w, wpk, cout, cout_pad, taps, bias=bias, stride=stride,
+                          residual=residual, out_gs=out_gs, debug=debug, debug_buf=debug_buf)
 
 
 def attn_fwd(x: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, wqkv: Tensor, bqkv: Tensor, wout: Tensor,

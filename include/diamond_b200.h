@@ -34,28 +34,47 @@ long long dmd_launch_count(int reset);
 
 /* Replaces nn.Conv2d weight use (src/models/blocks.py:18-19,96): packs a torch-layout weight [Cout][CinReal][k][k]
  * into the fp16 tensor-core operand layout [taps][Cin/8][CoutPad][8].  c0_real/c0_store describe a zero-padded first
- * source (e.g. 15 real channels stored as 16); for a single unpadded source pass c0_real = c0_store = CinReal. */
+ * source (e.g. 15 real channels stored as a 16-channel operand); for an unpadded source pass c0_real = c0_store = CinReal. */
 int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
                          int c0_real, int c0_store, void* stream);
 
-typedef struct dmd_conv_desc {
+/* Activation operand ("PLC16": padded-linear, chunk-major fp16; layout in diamond_b200/csrc/conv_tc.cuh).  One pass over
+ * an NHWC fp32 tensor applies what the reference runs on a conv INPUT — GroupNorm (blocks.py:28) or AdaGroupNorm
+ * (blocks.py:41-45), SiLU (blocks.py:143-144), channel concat as two sources (blocks.py:174), nearest-2x upsample
+ * (blocks.py:109) — and writes the operand(s) the convolution consumes. */
+size_t dmd_plc16_bytes(int B, int H, int W, int C);   /* H, W: conv input size (after upsampling) */
+
+typedef struct dmd_prep_desc {
   const float* src0;     /* NHWC [B][Hs][Ws][C0] */
-  const float* src1;     /* NHWC [B][Hs][Ws][C1] or NULL  (channel concat, blocks.py:174) */
-  int C0, C1, Cin;       /* Cin = K extent per tap, multiple of 16, >= C0 + C1 */
+  const float* src1;     /* NHWC [B][Hs][Ws][C1] or NULL */
+  int C0, C1;            /* multiples of 8 */
   int B, Hs, Ws;
-  int upsample;          /* 1: nearest x2 before the conv (blocks.py:109) */
-  int taps;              /* 9 = 3x3 pad 1 ; 1 = 1x1 */
-  int stride;            /* 1 or 2 (blocks.py:96) */
-  int prologue;          /* 0 none ; 1 AdaGroupNorm (blocks.py:43-45) ; 2 affine GroupNorm (blocks.py:28) */
-  int silu;              /* SiLU after the prologue (blocks.py:119,143-144; inner_model.py:48) */
-  const double* stats0;  /* [B][C0/gs0][2] (sum, sumsq) of src0 over (Hs*Ws*gs0) */
+  int upsample;
+  int mode;              /* 0 raw ; 1 AdaGroupNorm ; 2 affine GroupNorm */
+  int silu;
+  const double* stats0;  /* [B][C0/gs0][2] (sum, sumsq) */
   const double* stats1;
   int gs0, gs1;
   const float* film;     /* [B][film_stride] ; scale at film_off + c, shift at film_off + (C0+C1) + c */
   int film_stride, film_off;
-  const float* gamma;    /* affine GroupNorm weight / bias [C0+C1] */
+  const float* gamma;    /* [C0+C1] */
   const float* beta;
   float eps;
+  void* dst0;            /* operand of src0: dmd_plc16_bytes(B, H, W, C0) */
+  void* dst1;
+  void* dst_raw0;        /* optional: the un-normalised operand as well (1x1 skip projection, blocks.py:133,142) */
+  void* dst_raw1;
+} dmd_prep_desc;
+
+int dmd_prep_act(const dmd_prep_desc* d, void* stream);
+
+typedef struct dmd_conv_desc {
+  const void* src0;      /* PLC16 operand, C0 channels */
+  const void* src1;      /* second operand (channel concat) or NULL */
+  int C0, C1;            /* multiples of 16 */
+  int B, H, W;           /* conv input size */
+  int taps;              /* 9 = 3x3 pad 1 ; 1 = 1x1 */
+  int stride;            /* 1 or 2 (blocks.py:96) */
   const void* wpk;       /* from dmd_pack_conv_weight */
   const float* bias;     /* [Cout] or NULL */
   int Cout, CoutPad;     /* CoutPad: multiple of 16, <= 128 */

@@ -65,7 +65,8 @@ def _run_conv(dev, b, h, w, c0, c1, cout, taps=9, upsample=False, stride=1, prol
     c0s = ops.round_up(c0, 8)
     s0 = ops.nchw_to_nhwc(x0.to(dev), c0s)
     s1 = ops.nchw_to_nhwc(x1.to(dev)) if c1 else None
-    wpk, cout_pad = ops.pack_conv_weight(wt.to(dev), cin_pad, c0_real=c0, c0_store=c0s)
+    cin_pad = ops.round_up(c0s, 16) + (ops.round_up(c1, 16) if c1 else 0)
+    wpk, cout_pad = ops.pack_conv_weight(wt.to(dev), cin_pad, c0_real=c0, c0_store=ops.round_up(c0s, 16))
     kw = {}
     if prologue:
         gs0 = gs if c0 % gs == 0 else c0
