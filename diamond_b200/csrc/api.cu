@@ -156,7 +156,9 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off; p->film_ctot = d->C0 + d->C1;
   p->gamma = d->gamma; p->beta = d->beta; p->eps = d->eps;
   const Plc g = plc_geometry(d->B, p->H, p->W);
-  DMD_CHECK(g.PH * g.PW >= kPrepPos, "prep: image too small");
+  DMD_CHECK(g.PH * g.PW >= 32, "prep: image too small");
+  p->pos_per_block = g.PH * g.PW >= 256 ? 256 : (g.PH * g.PW / 32) * 32;  // a block touches at most 2 images
+  DMD_CHECK(d->C0 / (d->gs0 > 0 ? d->gs0 : 8) <= 4 || d->mode == 0, "prep: at most 4 groups per source");
   DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "prep: problem too large for 32-bit position math");
   p->PW = g.PW; p->PH = g.PH; p->Q = g.Q; p->G = g.G; p->Qalloc = g.Qalloc; p->plane_bytes = (unsigned long long)g.Qalloc * 16;
   p->dPW.init(g.PW); p->dPH.init(g.PH);
@@ -164,7 +166,7 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   return 0;
 }
 static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
-  prep_act_kernel<<<dim3((p.Qalloc + kPrepPos - 1) / kPrepPos, 1, nsrc), kPrepThreads, 0, st>>>(p);
+  prep_act_kernel<<<dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), kPrepThreads, 0, st>>>(p);
   DMD_LAUNCH_OK();
   return 0;
 }

@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     const int ch_half = (nchunks + 1) >> 1;
     const int ch_begin = first_of_quarter ? 0 : ch_half, ch_end = first_of_quarter ? ch_half : nchunks;
     const int G = p.ostats ? p.Cout / p.ogs : 1;
-    const bool vec_ok = (p.Cout & 3) == 0;
     const int L4 = p.Cout >> 2;                // float4 per output row (vector path)
+    const bool vec_ok = (p.Cout & 3) == 0 && (L4 & (L4 - 1)) == 0 && L4 <= 32;  // 16/32/64/128 channels
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       const int q0 = (tile_begin + it) * kTileM;
@@ -308,31 +308,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       // ---- pass 2: staging -> (+residual) -> coalesced global stores, GroupNorm partial sums
       if (vec_ok) {
         float s[kStatSlots] = {0.f, 0.f, 0.f}, ss[kStatSlots] = {0.f, 0.f, 0.f};
-        const int total4 = kTileM * L4;
-        for (int idx = et; idx < total4; idx += kEpiThreads) {
-          const int row = idx / L4, c4 = idx - row * L4;
-          const int2 ri = rowinfo[row];
-          if (ri.x >= 0) {
-            float4 v = *reinterpret_cast<const float4*>(sStage + (size_t)row * L.stage_pitch + (size_t)c4 * 16);
-            const size_t off = (size_t)ri.x * p.Cout + (size_t)c4 * 4;
-            if (p.resid) {
-              const float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + off));
-              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-            }
-            *reinterpret_cast<float4*>(p.out + off) = v;
-            const float ps = (v.x + v.y) + (v.z + v.w);
-            const float pss = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        // L4 is a power of two (host-checked for the vector path): thread owns channel quad c4 of rows r0, r0+rstep, ...
+        const int lg = 31 - __clz(L4);
+        const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
+        const int iters = kTileM / rstep;  // 2..16, multiple of 2
+        for (int k0 = 0; k0 < iters; k0 += 4) {
+          int2 ri[4]; float4 v[4], rr[4];
+          // all shared-memory and residual loads of the batch first (latency overlaps), then the math and the stores
 #pragma unroll
-            for (int k = 0; k < kStatSlots; ++k) {
-              if (ri.y == k) { s[k] += ps; ss[k] += pss; }
+          for (int u = 0; u < 4; ++u) {
+            const int row = r0 + (k0 + u) * rstep;
+            ri[u] = (k0 + u < iters) ? rowinfo[row] : make_int2(-1, 0);
+            rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ri[u].x >= 0) {
+              v[u] = *reinterpret_cast<const float4*>(sStage + (size_t)row * L.stage_pitch + (size_t)c4 * 16);
+              if (p.resid) rr[u] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (ri[u].x >= 0) {
+              float4 o = v[u];
+              o.x += rr[u].x; o.y += rr[u].y; o.z += rr[u].z; o.w += rr[u].w;
+              *reinterpret_cast<float4*>(p.out + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4) = o;
+              const float ps = (o.x + o.y) + (o.z + o.w);
+              const float pss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+#pragma unroll
+              for (int k = 0; k < kStatSlots; ++k) {
+                if (ri[u].y == k) { s[k] += ps; ss[k] += pss; }
+              }
             }
           }
         }
         if (p.ostats != nullptr) {
           // host guarantees L4 in {4, 8, 16, 32} (so 256 % L4 == 0): a thread's channel quad, hence its group, is fixed
-          const int c4 = et % L4;
           const int ogrp = (c4 * 4) / p.ogs;
           const int lanes_per_group = p.ogs >> 2;   // lanes (float4s) covering one group inside a row
+          // most tiles touch one image: skip the reductions of unused image slots (warp-uniform test)
+          bool used[kStatSlots];
+#pragma unroll
+          for (int k = 0; k < kStatSlots; ++k) used[k] = __any_sync(0xffffffffu, ss[k] != 0.f);
           bool leader = true;
 #pragma unroll
           for (int m = 1; m < 32; m <<= 1) {
@@ -341,8 +356,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             if (same) {
 #pragma unroll
               for (int k = 0; k < kStatSlots; ++k) {
-                s[k] += __shfl_xor_sync(0xffffffffu, s[k], m);
-                ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], m);
+                if (used[k]) {
+                  s[k] += __shfl_xor_sync(0xffffffffu, s[k], m);
+                  ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], m);
+                }
               }
               if (lane & m) leader = false;
             }
@@ -416,74 +433,123 @@ struct PrepParams {
   float eps;
   int PW, PH, Q, G, Qalloc;
   unsigned long long plane_bytes;
+  int pos_per_block;
   FastDiv dPW, dPH;
 };
 
 constexpr int kPrepThreads = 256;
-constexpr int kPrepPos = 32;  // positions per block
+constexpr int kPrepBatch = 2;
 
-__global__ void __launch_bounds__(kPrepThreads) prep_act_kernel(const PrepParams p) {
+// p.pos_per_block positions per block (multiple of 32, chosen by the host so that a block touches at most 2 images)
+__global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepParams p) {
   __shared__ float sa[2][kMaxCin], sb[2][kMaxCin];  // coefficients for the (at most 2) images this block touches
+  __shared__ float smr[2][4][2];                    // (mean, rstd) per (image slot, group)
   const PrepSrc& S = p.s[blockIdx.z];
   const int nch = S.Cpad >> 3;
-  const int pa0 = blockIdx.x * kPrepPos;            // first allocation position of this block
+  const int pa0 = blockIdx.x * p.pos_per_block;     // first allocation position of this block
   const int q_first = pa0 - p.G;
   const int n0 = q_first > 0 ? (int)p.dPH.div(p.dPW.div((uint32_t)min(q_first, p.Q - 1))) : 0;
   if (p.mode != 0) {
-    for (int e = threadIdx.x; e < 2 * S.C; e += kPrepThreads) {
-      const int slot = e / S.C, c = e - slot * S.C;
+    const int G = S.C / S.gs;
+    if (threadIdx.x < 2 * G) {  // fp64 only for the statistics
+      const int slot = threadIdx.x / G, g = threadIdx.x - slot * G;
       const int n = n0 + slot;
-      float a = 0.f, b = 0.f;
+      float mean_f = 0.f, rstd_f = 0.f;
       if (n < p.B) {
-        const int G = S.C / S.gs;
-        const double* st = S.stats + ((size_t)n * G + c / S.gs) * 2;
+        const double* st = S.stats + ((size_t)n * G + g) * 2;
         const double cnt = (double)p.Hs * p.Ws * S.gs;
         const double mean = st[0] / cnt;
         double var = st[1] / cnt - mean * mean;
         var = var > 0.0 ? var : 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-        const int cg = S.c_offset + c;
-        float sc, sh;
-        if (p.mode == 1) {
-          const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
-          sc = 1.f + __ldg(f + cg);
-          sh = __ldg(f + p.film_ctot + cg);
-        } else {
-          sc = __ldg(p.gamma + cg);
-          sh = __ldg(p.beta + cg);
-        }
-        a = rstd * sc;
-        b = sh - (float)mean * a;
+        mean_f = (float)mean;
+        rstd_f = (float)(1.0 / sqrt(var + (double)p.eps));
       }
-      sa[slot][c] = a;
-      sb[slot][c] = b;
+      smr[slot][g][0] = mean_f;
+      smr[slot][g][1] = rstd_f;
+    }
+    // FiLM / affine loads do not depend on the statistics: issue them before the barrier
+    float sc[2] = {0.f, 0.f}, sh[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = threadIdx.x + k * kPrepThreads;
+      if (e < 2 * S.C) {
+        const int slot = e / S.C, c = e - slot * S.C;
+        const int n = n0 + slot, cg = S.c_offset + c;
+        if (n < p.B) {
+          if (p.mode == 1) {
+            const float* f = p.film + (size_t)n * p.film_stride + p.film_off;
+            sc[k] = 1.f + __ldg(f + cg);
+            sh[k] = __ldg(f + p.film_ctot + cg);
+          } else {
+            sc[k] = __ldg(p.gamma + cg);
+            sh[k] = __ldg(p.beta + cg);
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = threadIdx.x + k * kPrepThreads;
+      if (e < 2 * S.C) {
+        const int slot = e / S.C, c = e - slot * S.C;
+        const float mean = smr[slot][c / S.gs][0], rstd = smr[slot][c / S.gs][1];
+        const float a = rstd * sc[k];
+        sa[slot][c] = a;
+        sb[slot][c] = sh[k] - mean * a;
+      }
     }
     __syncthreads();
   }
-  // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row)
-  for (int i = threadIdx.x; i < kPrepPos * nch; i += kPrepThreads) {
-    const int pl = i / nch, j = i - pl * nch;
-    const int pa = pa0 + pl;
-    if (pa >= p.Qalloc) continue;
-    const int q = pa - p.G;
-    uint4 packed = make_uint4(0u, 0u, 0u, 0u), raw = packed;
-    if (q >= 0 && q < p.Q && j * 8 < S.C) {
-      const uint32_t R = p.dPW.div((uint32_t)q);
-      const int x = q - (int)R * p.PW;
-      const uint32_t n = p.dPH.div(R);
-      const int y = (int)R - (int)n * p.PH;
-      if (x < p.W && y < p.H) {
-        const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-        const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
-        const float4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
-        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row).
+  // Items are processed in batches of kPrepBatch with all loads issued first (memory-level parallelism).
+  const int items = p.pos_per_block * nch;
+  for (int i0 = threadIdx.x; i0 < items; i0 += kPrepBatch * kPrepThreads) {
+    float4 v0[kPrepBatch], v1[kPrepBatch];
+    int meta[kPrepBatch];  // -1: zero fill, else image slot
+    size_t off[kPrepBatch];
+#pragma unroll
+    for (int u = 0; u < kPrepBatch; ++u) {
+      const int i = i0 + u * kPrepThreads;
+      meta[u] = -2;  // -2: out of range, nothing to write
+      if (i < items) {
+        const int pl = i / nch, j = i - pl * nch;
+        const int pa = pa0 + pl;
+        if (pa < p.Qalloc) {
+          meta[u] = -1;
+          off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
+          const int q = pa - p.G;
+          if (q >= 0 && q < p.Q && j * 8 < S.C) {
+            const uint32_t R = p.dPW.div((uint32_t)q);
+            const int x = q - (int)R * p.PW;
+            const uint32_t n = p.dPH.div(R);
+            const int y = (int)R - (int)n * p.PH;
+            if (x < p.W && y < p.H) {
+              const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
+              const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
+              v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
+              meta[u] = ((int)n - n0) | (j << 8);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPrepBatch; ++u) {
+      if (meta[u] == -2) continue;
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u), raw = packed;
+      if (meta[u] >= 0) {
+        const int slot = meta[u] & 0xff, j = meta[u] >> 8;
+        float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
         if (S.dst_raw != nullptr) {
           raw.x = pack_h2(v[0], v[1]); raw.y = pack_h2(v[2], v[3]); raw.z = pack_h2(v[4], v[5]); raw.w = pack_h2(v[6], v[7]);
         }
         if (p.mode != 0) {
-          const int slot = (int)n - n0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = fmaf(sa[slot][j * 8 + k], v[k], sb[slot][j * 8 + k]);
+          const float4* ca = reinterpret_cast<const float4*>(&sa[slot][j * 8]);
+          const float4* cb = reinterpret_cast<const float4*>(&sb[slot][j * 8]);
+          const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
+          v[0] = fmaf(a0.x, v[0], b0.x); v[1] = fmaf(a0.y, v[1], b0.y); v[2] = fmaf(a0.z, v[2], b0.z); v[3] = fmaf(a0.w, v[3], b0.w);
+          v[4] = fmaf(a1.x, v[4], b1.x); v[5] = fmaf(a1.y, v[5], b1.y); v[6] = fmaf(a1.z, v[6], b1.z); v[7] = fmaf(a1.w, v[7], b1.w);
         }
         if (p.act) {
 #pragma unroll
@@ -491,10 +557,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_act_kernel(const PrepParams
         }
         packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]); packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
       }
+      *reinterpret_cast<uint4*>(S.dst + off[u]) = packed;
+      if (S.dst_raw != nullptr) *reinterpret_cast<uint4*>(S.dst_raw + off[u]) = raw;
     }
-    const size_t off = (size_t)j * p.plane_bytes + (size_t)pa * 16;
-    *reinterpret_cast<uint4*>(S.dst + off) = packed;
-    if (S.dst_raw != nullptr) *reinterpret_cast<uint4*>(S.dst_raw + off) = raw;
   }
 }
 
