@@ -123,13 +123,27 @@ static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (nev
   return 0;
 }
 
+// Launch with programmatic stream serialization: the kernel may become resident while its predecessor drains and runs
+// its prologue up to griddepcontrol.wait.  Captured into CUDA graphs as a programmatic dependency edge.
+template <typename Kernel, typename Params>
+static int launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Params& p) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DMD_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
 template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
-  conv_tc_kernel<kCols><<<grid, kConvThreads, smem, st>>>(p);
-  DMD_LAUNCH_OK();
-  return 0;
+  return launch_pdl(conv_tc_kernel<kCols>, dim3(grid), dim3(kConvThreads), smem, st, p);
 }
 
 // ---- prep (GroupNorm / AdaGroupNorm / SiLU / upsample -> PLC16 operand)
@@ -166,9 +180,7 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   return 0;
 }
 static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
-  prep_act_kernel<<<dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), kPrepThreads, 0, st>>>(p);
-  DMD_LAUNCH_OK();
-  return 0;
+  return launch_pdl(prep_act_kernel, dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), dim3(kPrepThreads), 0, st, p);
 }
 extern "C" int dmd_prep_act(const dmd_prep_desc* d, void* stream) {
   PrepParams p; int nsrc;

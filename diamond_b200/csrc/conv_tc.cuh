@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   const int tile_begin = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
   const int my_tiles = tiles_lo + ((int)blockIdx.x < tiles_rem ? 1 : 0);
 
-  // ---- setup
+  // ---- setup (independent of the previous kernel: overlaps its tail under programmatic dependent launch)
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // operands / residual / statistics come from earlier kernels
 
   if (warp == 0) {
     // =========================================================================================== PRODUCER (TMA)
@@ -444,6 +446,8 @@ constexpr int kPrepBatch = 2;
 __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepParams p) {
   __shared__ float sa[2][kMaxCin], sb[2][kMaxCin];  // coefficients for the (at most 2) images this block touches
   __shared__ float smr[2][4][2];                    // (mean, rstd) per (image slot, group)
+  pdl_launch_dependents();
+  pdl_wait();
   const PrepSrc& S = p.s[blockIdx.z];
   const int nch = S.Cpad >> 3;
   const int pa0 = blockIdx.x * p.pos_per_block;     // first allocation position of this block

@@ -139,6 +139,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start
+// its prologue now.  wait: block until the previous kernel has completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small math
 // SiLU with the bare SFU approximations (5 instructions): v * rcp(1 + 2^(-v*log2 e)).  ex2/rcp.approx.ftz carry ~2 ulp;
 // 1 + e >= 1 so rcp needs no range fix-up (e = +inf -> 0), unlike __fdividef / __expf which add ~4 instructions each.
