@@ -16,6 +16,7 @@ class PrepDesc(C.Structure):
         ("mode", _i), ("silu", _i), ("stats0", _vp), ("stats1", _vp), ("gs0", _i), ("gs1", _i),
         ("film", _vp), ("film_stride", _i), ("film_off", _i), ("gamma", _vp), ("beta", _vp), ("eps", _f),
         ("dst0", _vp), ("dst1", _vp), ("dst_raw0", _vp), ("dst_raw1", _vp),
+        ("dst_lo0", _vp), ("dst_lo1", _vp), ("dst_raw_lo0", _vp), ("dst_raw_lo1", _vp),
     ]
 
 
@@ -24,6 +25,7 @@ class ConvDesc(C.Structure):
         ("src0", _vp), ("src1", _vp), ("C0", _i), ("C1", _i), ("B", _i), ("H", _i), ("W", _i), ("taps", _i), ("stride", _i),
         ("wpk", _vp), ("bias", _vp), ("Cout", _i), ("CoutPad", _i),
         ("residual", _vp), ("out", _vp), ("out_stats", _vp), ("out_gs", _i), ("debug", _i), ("debug_buf", _vp),
+        ("precise", _i), ("src0_lo", _vp), ("src1_lo", _vp),
     ]
 
 
@@ -54,7 +56,7 @@ SIGNATURES = {
     "dmd_version": (_i, []),
     "dmd_last_error": (C.c_char_p, []),
     "dmd_launch_count": (C.c_longlong, [_i]),
-    "dmd_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dmd_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dmd_plc16_bytes": (_sz, [_i, _i, _i, _i]),
     "dmd_prep_act": (_i, [C.POINTER(PrepDesc), _vp]),
     "dmd_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp]),

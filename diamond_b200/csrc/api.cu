@@ -70,9 +70,20 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   DMD_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   DMD_CHECK(d->C0 > 0 && d->C0 % 16 == 0 && d->C1 % 16 == 0 && d->C0 + d->C1 <= kMaxCin, "conv: operand channels must be multiples of 16, total <= %d (C0=%d C1=%d)", kMaxCin, d->C0, d->C1);
   DMD_CHECK((d->C1 == 0) == (d->src1 == nullptr), "conv: src1/C1 mismatch");
+  if (d->precise) DMD_CHECK(d->src0_lo && ((d->C1 == 0) == (d->src1_lo == nullptr)), "conv: precise mode needs the low operand parts");
   DMD_CHECK(d->CoutPad % 16 == 0 && d->CoutPad >= 16 && d->CoutPad <= 128 && d->Cout <= d->CoutPad && d->Cout > 0, "conv: bad Cout=%d CoutPad=%d", d->Cout, d->CoutPad);
   memset(p, 0, sizeof(*p));
-  p->src0 = (const uint8_t*)d->src0; p->src1 = (const uint8_t*)d->src1; p->C0 = d->C0; p->C1 = d->C1; p->Cin = d->C0 + d->C1;
+  {
+    const uint8_t* hi[2] = {(const uint8_t*)d->src0, (const uint8_t*)d->src1};
+    const uint8_t* lo[2] = {(const uint8_t*)d->src0_lo, (const uint8_t*)d->src1_lo};
+    const int cs[2] = {d->C0, d->C1};
+    const int nsrc = d->C1 ? 2 : 1;
+    int n = 0;
+    for (int rep = 0; rep < (d->precise ? 3 : 1); ++rep)  // [hi | lo | hi] against weights [W_hi | W_hi | W_lo]
+      for (int k = 0; k < nsrc; ++k) { p->seg_base[n] = (rep == 1) ? lo[k] : hi[k]; p->seg_slabs[n] = cs[k] / 16; ++n; }
+    p->nseg = n;
+    p->Cin = (d->C0 + d->C1) * (d->precise ? 3 : 1);
+  }
   p->B = d->B; p->H = d->H; p->W = d->W; p->taps = d->taps; p->stride = d->stride;
   if (d->stride == 2) DMD_CHECK(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H,W");
   p->wpk = reinterpret_cast<const __half*>(d->wpk); p->bias = d->bias; p->Cout = d->Cout; p->CoutPad = d->CoutPad;
@@ -155,6 +166,9 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   memset(p, 0, sizeof(*p));
   p->s[0].src = d->src0; p->s[0].C = d->C0; p->s[0].Cpad = round_up(d->C0, 16); p->s[0].stats = d->stats0; p->s[0].gs = d->gs0 > 0 ? d->gs0 : 8;
   p->s[0].c_offset = 0; p->s[0].dst = (uint8_t*)d->dst0; p->s[0].dst_raw = (uint8_t*)d->dst_raw0;
+  p->s[0].dst_lo = (uint8_t*)d->dst_lo0; p->s[0].dst_raw_lo = (uint8_t*)d->dst_raw_lo0;
+  p->s[1].dst_lo = (uint8_t*)d->dst_lo1; p->s[1].dst_raw_lo = (uint8_t*)d->dst_raw_lo1;
+  DMD_CHECK(!(d->dst_raw_lo0 && !d->dst_raw0) && !(d->dst_raw_lo1 && !d->dst_raw1), "prep: raw low part needs the raw operand too");
   p->s[1].src = d->src1; p->s[1].C = d->C1; p->s[1].Cpad = round_up(d->C1 > 0 ? d->C1 : 16, 16); p->s[1].stats = d->stats1; p->s[1].gs = d->gs1 > 0 ? d->gs1 : 8;
   p->s[1].c_offset = d->C0; p->s[1].dst = (uint8_t*)d->dst1; p->s[1].dst_raw = (uint8_t*)d->dst_raw1;
   if (d->mode) {
@@ -203,10 +217,10 @@ extern "C" int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream) {
 }
 
 extern "C" int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
-                                    int c0_real, int c0_store, void* stream) {
+                                    int c0_real, int c0_store, int precise, void* stream) {
   DMD_CHECK(w && wpk, "pack: null pointer");
-  const int total = taps * Cin * CoutPad;
-  pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store);
+  const int total = taps * Cin * CoutPad * (precise ? 3 : 1);
+  pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store, precise ? 1 : 0);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -269,6 +283,7 @@ constexpr float kGnEps = 1e-5f;  // blocks.py:13
 struct ConvW {          // one nn.Conv2d
   int w_idx, b_idx;     // indices into the state_dict pointer list
   int Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store;
+  int precise = 0;      // split-fp16: K = 3 * Cin
   size_t pk_off;        // byte offset into the packed-weight buffer
 };
 struct FilmW { int w_idx, b_idx, C, off; };  // AdaGroupNorm.linear ; off = row offset into the batched FiLM GEMM
@@ -283,7 +298,7 @@ struct Tens { float* data; double* stats; int C, H, W, gs; };
 
 enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2 };
 struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; };
-constexpr int kScratchSlots = 8;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
+constexpr int kScratchSlots = 10;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
 
 struct Plan {
   int B = 0, H = 0, W = 0;
@@ -333,11 +348,11 @@ namespace {
 
 struct Walker {  // assigns state_dict indices in module registration order and packed-buffer offsets
   dmd_denoiser* h; int idx = 0; size_t pk = 0;
-  ConvW conv(int cout, int cin_real, int taps, int c0_real, int c0_store, int c1) {
+  ConvW conv(int cout, int cin_real, int taps, int c0_real, int c0_store, int c1, int precise = 0) {
     ConvW c; c.w_idx = idx++; c.b_idx = idx++;
     c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
-    c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16);
-    c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2; pk = (pk + 255) & ~(size_t)255;
+    c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16); c.precise = precise;
+    c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2 * (precise ? 3 : 1); pk = (pk + 255) & ~(size_t)255;
     return c;
   }
   FilmW film(int C) { FilmW f; f.w_idx = idx++; f.b_idx = idx++; f.C = C; f.off = h->film_rows; h->film_rows += 2 * C; return f; }
@@ -345,7 +360,7 @@ struct Walker {  // assigns state_dict indices in module registration order and 
   ResBlockW resblock(int c0, int c1, int cout, bool attn) {
     ResBlockW r; r.cin = c0 + c1; r.cout = cout;
     r.has_proj = (r.cin != cout);
-    if (r.has_proj) r.proj = conv(cout, r.cin, 1, c0, c0, c1);
+    if (r.has_proj) r.proj = conv(cout, r.cin, 1, c0, c0, c1, 1);  // raw residual stream -> split-fp16
     r.n1 = film(r.cin);
     r.c1 = conv(cout, r.cin, 9, c0, c0, c1);
     r.n2 = film(cout);
@@ -366,7 +381,7 @@ int build_structure(dmd_denoiser* h) {
   h->i_cp0w = w.idx++; h->i_cp0b = w.idx++; h->i_cp2w = w.idx++; h->i_cp2b = w.idx++;
   const int cin_real = (c.num_steps_conditioning + 1) * c.img_channels;
   const int cin_store = round_up(cin_real, 16);
-  h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0);
+  h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0, 1);
   h->d_blocks.resize(L);
   for (int i = 0; i < L; ++i) {
     const int c1 = c.channels[i > 0 ? i - 1 : 0], c2 = c.channels[i];
@@ -388,7 +403,7 @@ int build_structure(dmd_denoiser* h) {
   for (int i = 1; i < L; ++i) h->downs[i] = w.conv(c.channels[i - 1], c.channels[i - 1], 9, c.channels[i - 1], c.channels[i - 1], 0);
   for (int m = 1; m < L; ++m) { const int ch = c.channels[L - 1 - m]; h->ups[m] = w.conv(ch, ch, 9, ch, ch, 0); }
   h->i_normout_w = w.idx++; h->i_normout_b = w.idx++;
-  h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0);
+  h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0, 1);
   h->n_tensors = w.idx;
   size_t pk = w.pk;
   h->film_w_off = pk; pk += (size_t)h->film_rows * c.cond_channels * 4; pk = (pk + 255) & ~(size_t)255;
@@ -415,7 +430,7 @@ struct PlanBuilder {
   const float* P(int idx) const { return h->ptrs.empty() ? nullptr : h->ptrs[idx]; }
 
   // PLC16 operands produced by one prep launch
-  struct Operand { uint8_t* n0 = nullptr; uint8_t* n1 = nullptr; uint8_t* r0 = nullptr; uint8_t* r1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0; };
+  struct Operand { uint8_t *n0 = nullptr, *n1 = nullptr, *r0 = nullptr, *r1 = nullptr, *nl0 = nullptr, *rl0 = nullptr, *rl1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0; };
 
   uint8_t* scratch() {
     uint8_t* p = pl->scratch[pl->scratch_next];
@@ -424,7 +439,8 @@ struct PlanBuilder {
   }
 
   // mode 0 raw / 1 AdaGroupNorm(film) / 2 GroupNorm(gamma,beta); also_raw: additionally emit the raw operand (skip projection)
-  Operand prep(const Tens& a, const Tens* b, int upsample, int mode, const FilmW* film, int gamma_idx, int beta_idx, bool silu, bool also_raw) {
+  // split: also emit the low fp16 part of the operand that a precise conv will read (raw if also_raw, else the main one)
+  Operand prep(const Tens& a, const Tens* b, int upsample, int mode, const FilmW* film, int gamma_idx, int beta_idx, bool silu, bool also_raw, bool split = false) {
     Operand o;
     dmd_prep_desc d; memset(&d, 0, sizeof(d));
     d.src0 = a.data ? a.data : (const float*)1; d.C0 = a.C; d.src1 = b ? (b->data ? b->data : (const float*)1) : nullptr; d.C1 = b ? b->C : 0;
@@ -439,6 +455,8 @@ struct PlanBuilder {
     o.n0 = scratch(); d.dst0 = o.n0;
     if (b) { o.n1 = scratch(); d.dst1 = o.n1; }
     if (also_raw) { o.r0 = scratch(); d.dst_raw0 = o.r0; if (b) { o.r1 = scratch(); d.dst_raw1 = o.r1; } }
+    if (split && also_raw) { o.rl0 = scratch(); d.dst_raw_lo0 = o.rl0; if (b) { o.rl1 = scratch(); d.dst_raw_lo1 = o.rl1; } }
+    if (split && !also_raw) { o.nl0 = scratch(); d.dst_lo0 = o.nl0; }
     o.C0 = round_up(a.C, 16); o.C1 = b ? round_up(b->C, 16) : 0;
     o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
     Op op; op.kind = OP_PREP;
@@ -450,11 +468,14 @@ struct PlanBuilder {
   void conv(const ConvW& cw, const Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats) {
     dmd_conv_desc d; memset(&d, 0, sizeof(d));
     d.src0 = raw ? in.r0 : in.n0; d.src1 = in.C1 ? (raw ? in.r1 : in.n1) : nullptr;
+    d.precise = cw.precise;
+    if (cw.precise) { d.src0_lo = raw ? in.rl0 : in.nl0; d.src1_lo = in.C1 ? in.rl1 : nullptr; }
     d.C0 = in.C0; d.C1 = in.C1; d.B = pl->B; d.H = in.H; d.W = in.W; d.taps = cw.taps; d.stride = stride;
     d.wpk = h->packed ? h->packed + cw.pk_off : (const void*)1; d.bias = P(cw.b_idx);
     d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
     d.residual = resid ? (resid->data ? resid->data : (const float*)1) : nullptr; d.out = out.data ? out.data : (float*)1;
     d.out_stats = out_stats ? (out.stats ? out.stats : (double*)1) : nullptr; d.out_gs = out.gs;
+    if (cw.precise && (!d.src0_lo || (in.C1 && !d.src1_lo))) { fail("plan: precise conv without low operand parts"); err = 1; return; }
     if (in.C0 + in.C1 != cw.Cin) { fail("plan: operand channels %d+%d do not match the packed weights (%d)", in.C0, in.C1, cw.Cin); err = 1; return; }
     Op op; op.kind = OP_CONV;
     if (conv_fill(&d, &op.conv, &op.smem, &op.cols)) { err = 1; return; }
@@ -464,7 +485,7 @@ struct PlanBuilder {
   // ResBlock.forward (blocks.py:141-147)
   Tens resblock(const ResBlockW& rb, const Tens& x, const Tens* skip) {
     const int H = x.H, W = x.W;
-    Operand in1 = prep(x, skip, 0, 1, &rb.n1, 0, 0, true, rb.has_proj != 0);
+    Operand in1 = prep(x, skip, 0, 1, &rb.n1, 0, 0, true, rb.has_proj != 0, rb.has_proj != 0);
     Tens r;
     if (rb.has_proj) { r = tensor(rb.cout, H, W, false); conv(rb.proj, in1, true, 1, nullptr, r, false); }
     else r = x;
@@ -501,7 +522,7 @@ struct PlanBuilder {
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
     Tens x = tensor(c.channels[0], H, W, true);
-    conv(h->conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 1, nullptr, x, true);
+    conv(h->conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true), false, 1, nullptr, x, true);
     std::vector<std::vector<Tens>> d_outputs;
     for (int i = 0; i < L; ++i) {
       Tens xd = x;
@@ -530,7 +551,7 @@ struct PlanBuilder {
     pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
     Tens f{pl->fout, nullptr, pl->CF, H, W, pl->CF};
     // conv_out(silu(norm_out(x)))  (inner_model.py:48)
-    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false), false, 1, nullptr, f, false);
+    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false, true), false, 1, nullptr, f, false);
     // sampler buffers
     const size_t img = (size_t)B * c.img_channels * H * W * 4;
     pl->s_obs = (float*)bump->take(img * c.num_steps_conditioning);
@@ -629,7 +650,7 @@ extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_ten
 extern "C" size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h) { return h->packed_bytes; }
 
 static int pack_one(dmd_denoiser* h, const ConvW& c, cudaStream_t st) {
-  return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, st);
+  return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.precise, st);
 }
 static int pack_rb(dmd_denoiser* h, const ResBlockW& r, cudaStream_t st) {
   const int CC = h->cfg.cond_channels;
@@ -906,7 +927,7 @@ extern "C" int dmd_actor_critic_set_weights(dmd_actor_critic* h, const float* co
   h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
   h->packed = (uint8_t*)packed;
   auto pack = [&](const ConvW& c) {
-    return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, stream);
+    return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, 0, stream);
   };
   if (pack(h->conv0)) return 1;
   for (auto& lv : h->levels) { if (pack(lv.conv)) return 1; if (lv.has_skip && pack(lv.skip)) return 1; }

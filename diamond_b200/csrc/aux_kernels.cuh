@@ -382,20 +382,25 @@ __global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict
 // Input channel ci of the packed tensor maps to real channel ci if ci < c0_real, zero if c0_real <= ci < c0_store,
 // and c0_real + (ci - c0_store) for the second source (concat), zero beyond.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ wpk, int Cout, int CoutPad,
-                                        int CinReal, int Cin, int taps, int c0_real, int c0_store) {
-  const int total = taps * Cin * CoutPad;
+                                        int CinReal, int Cin, int taps, int c0_real, int c0_store, int precise) {
+  // precise: K = 3*Cin laid out as [W_hi | W_hi | W_lo] to meet operands [A_hi | A_lo | A_hi] (split-fp16 product
+  // A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo, error ~2^-22 instead of 2^-11)
+  const int K = precise ? 3 * Cin : Cin;
+  const int total = taps * K * CoutPad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
     const int co = (i >> 3) % CoutPad;
-    const int j = (i >> 3) / CoutPad % (Cin >> 3);
-    const int t = (i >> 3) / CoutPad / (Cin >> 3);
-    const int ci = j * 8 + e;
+    const int j = (i >> 3) / CoutPad % (K >> 3);
+    const int t = (i >> 3) / CoutPad / (K >> 3);
+    const int kk = j * 8 + e;
+    const int seg = kk / Cin, ci = kk - seg * Cin;
     int cr = -1;
     if (ci < c0_store) cr = ci < c0_real ? ci : -1;
     else cr = c0_real + (ci - c0_store);
     float v = 0.f;
     if (co < Cout && cr >= 0 && cr < CinReal) v = w[((size_t)co * CinReal + cr) * taps + t];
-    wpk[i] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    wpk[i] = (seg < 2) ? hi : __float2half_rn(v - __half2float(hi));
   }
 }
 

@@ -32,7 +32,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = (2 + kEpiWarps) * 32;  // 320
 constexpr int kTileM = 128;
-constexpr int kMaxCin = 128;
+constexpr int kMaxCin = 128;        // channels of one activation source
+constexpr int kMaxKChannels = 384;  // K extent per tap: up to 3 x 128 (split-fp16 "precise" convs)
+constexpr int kMaxSegs = 6;
 constexpr int kMaxStages = 24;
 constexpr int kStatSlots = 3;   // images a 128-row tile can touch
 constexpr int kMaxOutGroups = 4;
@@ -59,10 +61,12 @@ __host__ __device__ inline Plc plc_geometry(int B, int H, int W) {
 }
 
 struct ConvParams {
-  const uint8_t* src0;  // PLC16 planes of the first source
-  const uint8_t* src1;  // second source (channel concat, blocks.py:174) or null
-  int C0, C1;           // channels per source (multiples of 16)
-  int Cin;              // C0 + C1
+  // K is a concatenation of up to 6 PLC16 operand segments: [x | skip] for a channel concat (blocks.py:174), and
+  // [x_hi | skip_hi | x_lo | skip_lo | x_hi | skip_hi] against weights [W_hi | W_hi | W_lo] for split-fp16 convs
+  const uint8_t* seg_base[kMaxSegs];
+  int seg_slabs[kMaxSegs];  // 16-channel slabs per segment
+  int nseg;
+  int Cin;              // total K channels per tap
   int B, H, W;          // conv input size
   int taps;             // 9 (3x3, pad 1) or 1 (1x1)
   int stride;           // 1 or 2 (stride 2 == stride-1 result sampled at even (y,x); exact for k=3,p=1)
@@ -162,24 +166,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     // =========================================================================================== PRODUCER (TMA)
     if (lane == 0) {
       const uint32_t chunk_bytes = (uint32_t)p.P * 16;
-      const int NA = p.C0 >> 3;  // chunk planes of the first source
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         // first halo position of this tile inside a plane (guard G keeps it non-negative)
         const size_t pos0 = (size_t)((tile_begin + it) * kTileM - halo + p.G) * 16;
+        int seg = 0, seg_ks = 0;  // current operand segment and slab index inside it
         for (int ks = 0; ks < kslabs; ++ks) {
-          DMD_TS(0, it, ks * 3 + 0);
+          DMD_TS(0, it, (ks & 3) * 3 + 0);
           mbar_wait(empty + stage, phase ^ 1u);
-          DMD_TS(0, it, ks * 3 + 1);
+          DMD_TS(0, it, (ks & 3) * 3 + 1);
           uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
           mbar_expect_tx(full + stage, 2 * chunk_bytes);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int j = 2 * ks + sub;
-            const uint8_t* plane = (j < NA) ? p.src0 + (size_t)j * p.plane_bytes : p.src1 + (size_t)(j - NA) * p.plane_bytes;
-            bulk_g2s(slab + (size_t)sub * p.Palloc * 16, plane + pos0, chunk_bytes, full + stage);
-          }
-          DMD_TS(0, it, ks * 3 + 2);
+          const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
+          bulk_g2s(slab, plane, chunk_bytes, full + stage);
+          bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+          DMD_TS(0, it, (ks & 3) * 3 + 2);
+          if (++seg_ks == p.seg_slabs[seg]) { seg_ks = 0; ++seg; }
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -217,9 +219,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
         uint32_t b_lo = b_lo0;
         for (int ks = 0; ks < kslabs; ++ks) {
-          DMD_TS(1, it, ks * 3 + 0);
+          DMD_TS(1, it, (ks & 3) * 3 + 0);
           mbar_wait(full + stage, phase);
-          DMD_TS(1, it, ks * 3 + 1);
+          DMD_TS(1, it, (ks & 3) * 3 + 1);
           tc_fence_after_sync();
           if (!(p.dbg & 2)) {
             if (p.taps == 9) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             }
           }
           umma_commit(empty + stage);  // slab reusable once these MMAs retire
-          DMD_TS(1, it, ks * 3 + 2);
+          DMD_TS(1, it, (ks & 3) * 3 + 2);
           b_lo += kstep16;
           a_lo += slab16;
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       const int b = it & 1;
       const int q0 = (tile_begin + it) * kTileM;
       const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
+      const int q_last = min(q0 + kTileM, p.Q) - 1;
+      const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;  // all rows of the tile in one image
       // ---- row bookkeeping (one thread per row)
       if (et < kTileM) {
         const int q = q0 + et;
@@ -280,6 +284,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           if (valid && !(p.dbg & 8)) { opix = (n * Ho + yo) * Wo + xo; slot = n - n_lo; }
         }
         rowinfo[et] = make_int2(opix, slot);
+      }
+      // ---- residual prefetch: it does not depend on the accumulator, so its latency hides behind the MMAs of this tile
+      const int lg = 31 - __clz(L4 > 0 ? L4 : 1);
+      const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
+      const int iters = vec_ok ? kTileM / rstep : 0;  // 2..16
+      float4 rpre[8];
+      const bool prefetch = vec_ok && p.resid != nullptr && iters <= 8;
+      if (prefetch) {
+        named_bar_sync(10, kEpiThreads);  // rowinfo visible
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          rpre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < iters) {
+            const int2 ri = rowinfo[r0 + u * rstep];
+            if (ri.x >= 0) rpre[u] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)ri.x * p.Cout + (size_t)c4 * 4));
+          }
+        }
       }
       // ---- pass 1: TMEM -> (+bias) -> staging
       if (et == 0) DMD_TS(2, it, 0);
@@ -311,33 +332,38 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (vec_ok) {
         float s[kStatSlots] = {0.f, 0.f, 0.f}, ss[kStatSlots] = {0.f, 0.f, 0.f};
         // L4 is a power of two (host-checked for the vector path): thread owns channel quad c4 of rows r0, r0+rstep, ...
-        const int lg = 31 - __clz(L4);
-        const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
-        const int iters = kTileM / rstep;  // 2..16, multiple of 2
-        for (int k0 = 0; k0 < iters; k0 += 4) {
-          int2 ri[4]; float4 v[4], rr[4];
-          // all shared-memory and residual loads of the batch first (latency overlaps), then the math and the stores
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int row = r0 + (k0 + u) * rstep;
-            ri[u] = (k0 + u < iters) ? rowinfo[row] : make_int2(-1, 0);
-            rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ri[u].x >= 0) {
-              v[u] = *reinterpret_cast<const float4*>(sStage + (size_t)row * L.stage_pitch + (size_t)c4 * 16);
-              if (p.resid) rr[u] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4));
+        for (int k0 = 0; k0 < 16; k0 += 4) {
+          if (k0 < iters) {
+            int2 ri[4]; float4 v[4], rr[4];
+            // all shared-memory (and, if not prefetched, residual) loads of the batch first, then the math and the stores
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = r0 + (k0 + u) * rstep;
+              ri[u] = (k0 + u < iters) ? rowinfo[row] : make_int2(-1, 0);
+              rr[u] = (prefetch && k0 + u < 8) ? rpre[(k0 + u) & 7] : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ri[u].x >= 0) {
+                v[u] = *reinterpret_cast<const float4*>(sStage + (size_t)row * L.stage_pitch + (size_t)c4 * 16);
+                if (p.resid && !prefetch) rr[u] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4));
+              }
             }
-          }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (ri[u].x >= 0) {
-              float4 o = v[u];
-              o.x += rr[u].x; o.y += rr[u].y; o.z += rr[u].z; o.w += rr[u].w;
-              *reinterpret_cast<float4*>(p.out + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4) = o;
-              const float ps = (o.x + o.y) + (o.z + o.w);
-              const float pss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+            for (int u = 0; u < 4; ++u) {
+              if (ri[u].x >= 0) {
+                float4 o = v[u];
+                o.x += rr[u].x; o.y += rr[u].y; o.z += rr[u].z; o.w += rr[u].w;
+                *reinterpret_cast<float4*>(p.out + (size_t)ri[u].x * p.Cout + (size_t)c4 * 4) = o;
+                if (p.ostats != nullptr) {
+                  const float ps = (o.x + o.y) + (o.z + o.w);
+                  const float pss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                  if (single_image) { s[0] += ps; ss[0] += pss; }
+                  else {
 #pragma unroll
-              for (int k = 0; k < kStatSlots; ++k) {
-                if (ri[u].y == k) { s[k] += ps; ss[k] += pss; }
+                    for (int k = 0; k < kStatSlots; ++k) {
+                      if (ri[u].y == k) { s[k] += ps; ss[k] += pss; }
+                    }
+                  }
+                }
               }
             }
           }
@@ -349,7 +375,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           // most tiles touch one image: skip the reductions of unused image slots (warp-uniform test)
           bool used[kStatSlots];
 #pragma unroll
-          for (int k = 0; k < kStatSlots; ++k) used[k] = __any_sync(0xffffffffu, ss[k] != 0.f);
+          for (int k = 0; k < kStatSlots; ++k) used[k] = (k == 0) ? true : (!single_image && __any_sync(0xffffffffu, ss[k] != 0.f));
           bool leader = true;
 #pragma unroll
           for (int m = 1; m < 32; m <<= 1) {
@@ -420,8 +446,10 @@ struct PrepSrc {
   const double* stats; // [B][C/gs][2] or null (mode 0)
   int gs;
   int c_offset;        // channel offset inside the concatenated norm input (FiLM / gamma index = c_offset + c)
-  uint8_t* dst;        // PLC16 planes, normalised/activated
+  uint8_t* dst;        // PLC16 planes, normalised/activated (fp16 "hi" part)
+  uint8_t* dst_lo;     // optional: fp16(y - hi), the low part for split-fp16 convs
   uint8_t* dst_raw;    // optional second output: the raw tensor in PLC16 (for the 1x1 skip projection), or null
+  uint8_t* dst_raw_lo; // optional: low part of the raw tensor
 };
 struct PrepParams {
   PrepSrc s[2];
@@ -441,6 +469,19 @@ struct PrepParams {
 
 constexpr int kPrepThreads = 256;
 constexpr int kPrepBatch = 2;
+
+// low parts of a split-fp16 operand: lo = fp16(v - float(hi))
+__device__ __forceinline__ uint4 pack_lo8(const float (&v)[8], const uint4& hi) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  uint4 lo;
+  uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(h[k]);
+    l[k] = pack_h2(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+  }
+  return lo;
+}
 
 // p.pos_per_block positions per block (multiple of 32, chosen by the host so that a block touches at most 2 images)
 __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepParams p) {
@@ -541,12 +582,13 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
 #pragma unroll
     for (int u = 0; u < kPrepBatch; ++u) {
       if (meta[u] == -2) continue;
-      uint4 packed = make_uint4(0u, 0u, 0u, 0u), raw = packed;
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u), raw = packed, packed_lo = packed, raw_lo = packed;
       if (meta[u] >= 0) {
         const int slot = meta[u] & 0xff, j = meta[u] >> 8;
         float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
         if (S.dst_raw != nullptr) {
           raw.x = pack_h2(v[0], v[1]); raw.y = pack_h2(v[2], v[3]); raw.z = pack_h2(v[4], v[5]); raw.w = pack_h2(v[6], v[7]);
+          if (S.dst_raw_lo != nullptr) raw_lo = pack_lo8(v, raw);
         }
         if (p.mode != 0) {
           const float4* ca = reinterpret_cast<const float4*>(&sa[slot][j * 8]);
@@ -560,9 +602,12 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
           for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
         }
         packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]); packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+        if (S.dst_lo != nullptr) packed_lo = pack_lo8(v, packed);
       }
       *reinterpret_cast<uint4*>(S.dst + off[u]) = packed;
+      if (S.dst_lo != nullptr) *reinterpret_cast<uint4*>(S.dst_lo + off[u]) = packed_lo;
       if (S.dst_raw != nullptr) *reinterpret_cast<uint4*>(S.dst_raw + off[u]) = raw;
+      if (S.dst_raw_lo != nullptr) *reinterpret_cast<uint4*>(S.dst_raw_lo + off[u]) = raw_lo;
     }
   }
 }

@@ -36,7 +36,8 @@ def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
     return out
 
 
-def pack_conv_weight(w: Tensor, cin_pad: int, c0_real: Optional[int] = None, c0_store: Optional[int] = None) -> Tuple[Tensor, int]:
+def pack_conv_weight(w: Tensor, cin_pad: int, c0_real: Optional[int] = None, c0_store: Optional[int] = None,
+                     precise: bool = False) -> Tuple[Tensor, int]:
     """torch weight [Cout][Cin][k][k] -> fp16 operand [taps][cin_pad/8][CoutPad][8]; returns (packed, CoutPad)."""
     _cuda(w)
     cout, cin, kh, kw = w.shape
@@ -44,9 +45,9 @@ def pack_conv_weight(w: Tensor, cin_pad: int, c0_real: Optional[int] = None, c0_
     cout_pad = round_up(cout, 16)
     c0_real = cin if c0_real is None else c0_real
     c0_store = c0_real if c0_store is None else c0_store
-    out = torch.empty(taps * cin_pad * cout_pad, device=w.device, dtype=torch.float16)
+    out = torch.empty(taps * cin_pad * cout_pad * (3 if precise else 1), device=w.device, dtype=torch.float16)
     _lib.check(_lib.lib().dmd_pack_conv_weight(w.data_ptr(), out.data_ptr(), cout, cout_pad, cin, cin_pad, taps,
-                                              c0_real, c0_store, _lib.current_stream()))
+                                              c0_real, c0_store, int(precise), _lib.current_stream()))
     return out, cout_pad
 
 
@@ -62,8 +63,9 @@ def gn_stats(x: Tensor, gs: int) -> Tensor:
 def prep_act(src0: Tensor, *, src1: Optional[Tensor] = None, upsample: bool = False, mode: int = 0, silu: bool = False,
              stats0: Optional[Tensor] = None, stats1: Optional[Tensor] = None, gs0: int = 0, gs1: int = 0,
              film: Optional[Tensor] = None, film_off: int = 0, gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None,
-             eps: float = 1e-5, also_raw: bool = False):
-    """NHWC fp32 -> PLC16 fp16 operand(s) with the conv-input transform fused.  Returns (n0, n1, r0, r1, H, W)."""
+             eps: float = 1e-5, also_raw: bool = False, split: bool = False):
+    """NHWC fp32 -> PLC16 fp16 operand(s) with the conv-input transform fused.  Returns (n0, n1, r0, r1, H, W); with
+    split=True the low fp16 parts of the main operands are returned as extra elements (l0, l1)."""
     _cuda(src0, src1, stats0, stats1, film, gamma, beta)
     lib = _lib.lib()
     b, hs, ws, c0 = src0.shape
@@ -82,14 +84,19 @@ def prep_act(src0: Tensor, *, src1: Optional[Tensor] = None, upsample: bool = Fa
     d.film, d.film_stride, d.film_off = _lib.ptr(film), (film.shape[1] if film is not None else 0), film_off
     d.gamma, d.beta, d.eps = _lib.ptr(gamma), _lib.ptr(beta), eps
     d.dst0, d.dst1, d.dst_raw0, d.dst_raw1 = n0.data_ptr(), _lib.ptr(n1), _lib.ptr(r0), _lib.ptr(r1)
+    l0, l1 = (buf(c0) if split else None), (buf(c1) if (split and c1) else None)
+    d.dst_lo0, d.dst_lo1 = _lib.ptr(l0), _lib.ptr(l1)
     _lib.check(lib.dmd_prep_act(C.byref(d), _lib.current_stream()))
+    if split:
+        return n0, n1, r0, r1, h, w, l0, l1
     return n0, n1, r0, r1, h, w
 
 
 def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h: int, w: int, wpk: Tensor, cout: int,
                    cout_pad: int, taps: int = 9, *, bias: Optional[Tensor] = None, stride: int = 1,
                    residual: Optional[Tensor] = None, out_gs: int = 0, out: Optional[Tensor] = None,
-                   ostats: Optional[Tensor] = None, debug: int = 0, debug_buf: Optional[Tensor] = None):
+                   ostats: Optional[Tensor] = None, debug: int = 0, debug_buf: Optional[Tensor] = None,
+                   lo0: Optional[Tensor] = None, lo1: Optional[Tensor] = None):
     """tcgen05 conv on already prepared PLC16 operand(s) (one kernel launch)."""
     _cuda(n0, n1, wpk, bias, residual)
     ho, wo = h // stride, w // stride
@@ -103,6 +110,7 @@ def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h
     d.wpk, d.bias, d.Cout, d.CoutPad = wpk.data_ptr(), _lib.ptr(bias), cout, cout_pad
     d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
     d.debug_buf = _lib.ptr(debug_buf)
+    d.precise, d.src0_lo, d.src1_lo = int(lo0 is not None), _lib.ptr(lo0), _lib.ptr(lo1)
     _lib.check(_lib.lib().dmd_conv2d_fprop(C.byref(d), _lib.current_stream()))
     return out, ostats
 
@@ -112,15 +120,19 @@ def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: i
                  prologue: int = 0, silu: bool = False, stats0: Optional[Tensor] = None, stats1: Optional[Tensor] = None,
                  gs0: int = 0, gs1: int = 0, film: Optional[Tensor] = None, film_off: int = 0,
                  gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
-                 residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0, debug_buf: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
-    """The reference's `conv(act(norm(cat(x, skip))))` on NHWC fp32 tensors: one prep launch + one tcgen05 conv launch."""
-    n0, n1, _, _, h, w = prep_act(src0, src1=src1, upsample=upsample, mode=prologue, silu=silu, stats0=stats0, stats1=stats1,
-                                  gs0=gs0, gs1=gs1, film=film, film_off=film_off, gamma=gamma, beta=beta, eps=eps)
+                 residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0, debug_buf: Optional[Tensor] = None,
+                 precise: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """The reference's `conv(act(norm(cat(x, skip))))` on NHWC fp32 tensors: one prep launch + one tcgen05 conv launch.
+    precise=True: split-fp16 operands (weights must be packed with precise=True)."""
+    res = prep_act(src0, src1=src1, upsample=upsample, mode=prologue, silu=silu, stats0=stats0, stats1=stats1,
+                   gs0=gs0, gs1=gs1, film=film, film_off=film_off, gamma=gamma, beta=beta, eps=eps, split=precise)
+    n0, n1, _, _, h, w = res[:6]
+    lo0, lo1 = (res[6], res[7]) if precise else (None, None)
     c0, c1 = round_up(src0.shape[3], 16), (round_up(src1.shape[3], 16) if src1 is not None else 0)
     if c0 + c1 != cin_pad:
         raise ValueError(f"operand channels {c0}+{c1} do not match the packed weights ({cin_pad})")
     return conv2d_operand(n0, n1, c0, c1, src0.shape[0], h, w, wpk, cout, cout_pad, taps, bias=bias, stride=stride,
-                          residual=residual, out_gs=out_gs, debug=debug, debug_buf=debug_buf)
+                          residual=residual, out_gs=out_gs, debug=debug, debug_buf=debug_buf, lo0=lo0, lo1=lo1)
 
 
 def attn_fwd(x: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, wqkv: Tensor, bqkv: Tensor, wout: Tensor,

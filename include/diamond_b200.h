@@ -36,7 +36,10 @@ long long dmd_launch_count(int reset);
  * into the fp16 tensor-core operand layout [taps][Cin/8][CoutPad][8].  c0_real/c0_store describe a zero-padded first
  * source (e.g. 15 real channels stored as a 16-channel operand); for an unpadded source pass c0_real = c0_store = CinReal. */
 int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
-                         int c0_real, int c0_store, void* stream);
+                         int c0_real, int c0_store, int precise, void* stream);
+/* precise = 1: split-fp16 packing [W_hi | W_hi | W_lo] (3*Cin channels per tap) for dmd_conv_desc.precise convs: the
+ * product is evaluated as A_hi W_hi + A_lo W_hi + A_hi W_lo on the tensor cores, i.e. to ~2^-22 instead of 2^-11.  Used
+ * for the layers whose input is the raw residual stream (1x1 skip projections, conv_in) and for conv_out. */
 
 /* Activation operand ("PLC16": padded-linear, chunk-major fp16; layout in diamond_b200/csrc/conv_tc.cuh).  One pass over
  * an NHWC fp32 tensor applies what the reference runs on a conv INPUT — GroupNorm (blocks.py:28) or AdaGroupNorm
@@ -64,6 +67,10 @@ typedef struct dmd_prep_desc {
   void* dst1;
   void* dst_raw0;        /* optional: the un-normalised operand as well (1x1 skip projection, blocks.py:133,142) */
   void* dst_raw1;
+  void* dst_lo0;         /* optional low parts (split-fp16): fp16(y - fp16(y)) of the transformed operand ... */
+  void* dst_lo1;
+  void* dst_raw_lo0;     /* ... and of the raw operand */
+  void* dst_raw_lo1;
 } dmd_prep_desc;
 
 int dmd_prep_act(const dmd_prep_desc* d, void* stream);
@@ -84,6 +91,9 @@ typedef struct dmd_conv_desc {
   int out_gs;
   int debug;             /* bring-up only; 0 */
   void* debug_buf;       /* bring-up only; NULL */
+  int precise;           /* 1: split-fp16 (needs src*_lo and weights packed with precise = 1) */
+  const void* src0_lo;
+  const void* src1_lo;
 } dmd_conv_desc;
 
 int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);

@@ -1,4 +1,4 @@
-"""Runs the dominant conv (3x3 64->64 @64x64, 32 images, AdaGN+SiLU prologue) a few times — target for ncu."""
+"""Runs the dominant conv pair (prep_act + conv_tc, 3x3 64->64 @64x64, 32 images, AdaGN+SiLU, residual, stats) — ncu target."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -27,7 +27,7 @@ def _h(x):
 
 
 def _run_conv(dev, b, h, w, c0, c1, cout, taps=9, upsample=False, stride=1, prologue=0, silu=False, residual=False,
-              want_stats=False, seed=0, debug=0):
+              want_stats=False, seed=0, debug=0, precise=False):
     from diamond_b200 import ops
 
     g = torch.Generator().manual_seed(seed)
@@ -66,7 +66,7 @@ def _run_conv(dev, b, h, w, c0, c1, cout, taps=9, upsample=False, stride=1, prol
     s0 = ops.nchw_to_nhwc(x0.to(dev), c0s)
     s1 = ops.nchw_to_nhwc(x1.to(dev)) if c1 else None
     cin_pad = ops.round_up(c0s, 16) + (ops.round_up(c1, 16) if c1 else 0)
-    wpk, cout_pad = ops.pack_conv_weight(wt.to(dev), cin_pad, c0_real=c0, c0_store=ops.round_up(c0s, 16))
+    wpk, cout_pad = ops.pack_conv_weight(wt.to(dev), cin_pad, c0_real=c0, c0_store=ops.round_up(c0s, 16), precise=precise)
     kw = {}
     if prologue:
         gs0 = gs if c0 % gs == 0 else c0
@@ -78,7 +78,7 @@ def _run_conv(dev, b, h, w, c0, c1, cout, taps=9, upsample=False, stride=1, prol
         prologue=prologue, silu=silu, film=film.to(dev) if film is not None else None, film_off=5,
         gamma=gamma.to(dev) if gamma is not None else None, beta=beta.to(dev) if beta is not None else None,
         residual=ops.nchw_to_nhwc(res.to(dev)) if residual else None,
-        out_gs=(32 if cout % 32 == 0 else 0) if want_stats else 0, debug=debug, **kw)
+        out_gs=(32 if cout % 32 == 0 else 0) if want_stats else 0, debug=debug, precise=precise, **kw)
     got = ops.nhwc_to_nchw(out).cpu()
     torch.cuda.synchronize()
     return got, ref32, ref16, (st.cpu() if st is not None else None)
@@ -121,6 +121,20 @@ def test_conv_fused_norm_prologue_residual_stats(prologue, silu, shape):
     v = got.double().reshape(b, c // 32, 32 * h * w)
     want = torch.stack([v.sum(-1), (v * v).sum(-1)], -1)
     assert torch.allclose(st, want, rtol=1e-5, atol=1e-3), float((st - want).abs().max())
+
+
+@pytest.mark.parametrize("case", [
+    dict(b=2, h=64, w=64, c0=64, c1=64, cout=64, taps=1),                    # u3.proj: raw residual stream, two sources
+    dict(b=2, h=64, w=64, c0=15, c1=0, cout=64),                             # conv_in
+    dict(b=2, h=64, w=64, c0=64, c1=0, cout=3, prologue=2, silu=True),       # conv_out(silu(norm_out(x)))
+    dict(b=3, h=16, w=16, c0=32, c1=64, cout=64, taps=1),                    # proj with unequal sources
+], ids=["proj", "conv_in", "conv_out", "proj96"])
+def test_conv_precise_split_fp16(case):
+    """split-fp16 (A_hi W_hi + A_lo W_hi + A_hi W_lo): the layers that feed the residual stream directly match the fp32
+    reference to ~1e-6 instead of the 4e-4 of single fp16 operands."""
+    dev = _dev()
+    got, ref32, _, _ = _run_conv(dev, precise=True, seed=5, **case)
+    assert _rel(got, ref32) < 5e-6, _rel(got, ref32)
 
 
 def test_conv_linearity_and_zero():
