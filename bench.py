@@ -333,7 +333,7 @@ def run_native(args):
         peaks, peaks_src = load_peaks()
         roof = conv_roofline(dev, B, peaks, peaks_src)
         cpu_envs = 4
-        if world == 1:
+        if world == 1 and not args.skip_cpu_baseline:
             cores, avail = pick_cpu_threads()
             cpu_val, cpu_times = cpu_frames_per_s(cpu_envs, 3, cores)
         else:
@@ -367,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=32, help="imagined environments per GPU (config/trainer.yaml actor_critic batch 32)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="development runs: omit the (minutes-long) cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

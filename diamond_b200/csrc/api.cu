@@ -163,6 +163,10 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   DMD_CHECK(d->C0 % 8 == 0 && d->C1 % 8 == 0 && d->C0 > 0 && d->C0 <= kMaxCin && d->C1 <= kMaxCin, "prep: channels must be multiples of 8 (C0=%d C1=%d)", d->C0, d->C1);
   DMD_CHECK((d->C1 == 0) == (d->src1 == nullptr) && (d->C1 == 0) == (d->dst1 == nullptr), "prep: src1/dst1/C1 mismatch");
   DMD_CHECK(d->mode >= 0 && d->mode <= 2, "prep: bad mode");
+  for (int c : {d->C0, d->C1 ? d->C1 : 16}) {
+    const int cp = round_up(c, 16);
+    DMD_CHECK(cp == 16 || cp == 32 || cp == 64 || cp == 128, "prep: a source must have <= 16/32/64/128 channels after padding (got %d)", c);
+  }
   memset(p, 0, sizeof(*p));
   p->s[0].src = d->src0; p->s[0].C = d->C0; p->s[0].Cpad = round_up(d->C0, 16); p->s[0].stats = d->stats0; p->s[0].gs = d->gs0 > 0 ? d->gs0 : 8;
   p->s[0].c_offset = 0; p->s[0].dst = (uint8_t*)d->dst0; p->s[0].dst_raw = (uint8_t*)d->dst_raw0;
@@ -403,7 +407,7 @@ int build_structure(dmd_denoiser* h) {
   for (int i = 1; i < L; ++i) h->downs[i] = w.conv(c.channels[i - 1], c.channels[i - 1], 9, c.channels[i - 1], c.channels[i - 1], 0);
   for (int m = 1; m < L; ++m) { const int ch = c.channels[L - 1 - m]; h->ups[m] = w.conv(ch, ch, 9, ch, ch, 0); }
   h->i_normout_w = w.idx++; h->i_normout_b = w.idx++;
-  h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0, 1);
+  h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0, 0);  // split-fp16 here costs 3x on an N=16 conv for 3.2e-4
   h->n_tensors = w.idx;
   size_t pk = w.pk;
   h->film_w_off = pk; pk += (size_t)h->film_rows * c.cond_channels * 4; pk = (pk + 255) & ~(size_t)255;
@@ -551,7 +555,7 @@ struct PlanBuilder {
     pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
     Tens f{pl->fout, nullptr, pl->CF, H, W, pl->CF};
     // conv_out(silu(norm_out(x)))  (inner_model.py:48)
-    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false, true), false, 1, nullptr, f, false);
+    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false, false), false, 1, nullptr, f, false);
     // sampler buffers
     const size_t img = (size_t)B * c.img_channels * H * W * 4;
     pl->s_obs = (float*)bump->take(img * c.num_steps_conditioning);

@@ -548,36 +548,41 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
   }
   // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row).
   // Items are processed in batches of kPrepBatch with all loads issued first (memory-level parallelism).
-  const int items = p.pos_per_block * nch;
-  for (int i0 = threadIdx.x; i0 < items; i0 += kPrepBatch * kPrepThreads) {
+  // thread = (chunk j, position lane); it walks positions pl, pl + pstep, ...  (x, y, n) are advanced incrementally, so the
+  // per-item cost of locating the source pixel is a few adds instead of two divisions
+  const int pstep = kPrepThreads / nch;             // nch in {2, 4, 8, 16}
+  const int j = threadIdx.x % nch;
+  int pl = threadIdx.x / nch;
+  int x, y, n;                                      // coordinates of position pa0 + pl (may be in the guard: q < 0)
+  {
+    const int q = pa0 + pl - p.G;
+    const int qq = q < 0 ? 0 : q;
+    const uint32_t R = p.dPW.div((uint32_t)qq);
+    x = qq - (int)R * p.PW; n = (int)p.dPH.div(R); y = (int)R - n * p.PH;
+    if (q < 0) x += q;                              // negative x marks guard positions until it wraps to >= 0
+  }
+  const bool has_data = j * 8 < S.C;
+  for (; pl < p.pos_per_block; pl += kPrepBatch * pstep) {
     float4 v0[kPrepBatch], v1[kPrepBatch];
-    int meta[kPrepBatch];  // -1: zero fill, else image slot
+    int meta[kPrepBatch];  // -2: nothing to write, -1: zero fill, else image slot | j << 8
     size_t off[kPrepBatch];
 #pragma unroll
     for (int u = 0; u < kPrepBatch; ++u) {
-      const int i = i0 + u * kPrepThreads;
-      meta[u] = -2;  // -2: out of range, nothing to write
-      if (i < items) {
-        const int pl = i / nch, j = i - pl * nch;
-        const int pa = pa0 + pl;
-        if (pa < p.Qalloc) {
-          meta[u] = -1;
-          off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
-          const int q = pa - p.G;
-          if (q >= 0 && q < p.Q && j * 8 < S.C) {
-            const uint32_t R = p.dPW.div((uint32_t)q);
-            const int x = q - (int)R * p.PW;
-            const uint32_t n = p.dPH.div(R);
-            const int y = (int)R - (int)n * p.PH;
-            if (x < p.W && y < p.H) {
-              const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-              const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
-              v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
-              meta[u] = ((int)n - n0) | (j << 8);
-            }
-          }
+      const int pa = pa0 + pl + u * pstep;
+      meta[u] = -2;
+      if (pl + u * pstep < p.pos_per_block && pa < p.Qalloc) {
+        meta[u] = -1;
+        off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
+        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
+          const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
+          const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
+          v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
+          meta[u] = (n - n0) | (j << 8);
         }
       }
+      // advance to the next owned position
+      x += pstep;
+      while (x >= p.PW) { x -= p.PW; if (++y == p.PH) { y = 0; ++n; } }
     }
 #pragma unroll
     for (int u = 0; u < kPrepBatch; ++u) {
