@@ -164,7 +164,7 @@ def workload_config(args, envs_override=None):
     return {"workload": "DiffusionSampler.sample: Breakout-shape imagination, frame-stack 4, 64x64x3, 3 Euler denoise steps, "
                         "default agent config (4.4 M-param U-Net), random-init de-zeroed weights",
             "envs_per_gpu": envs, "global_envs": envs * args.gpus, "parallelism": f"dp{args.gpus} (independent envs per rank, no collective)",
-            "l2": "256 MiB L2 flush between timed steps (untimed)", "cuda_graph": True}
+            "l2": "256 MiB L2 flush between timed steps (untimed)", "cuda_graph": True, "programmatic_dependent_launch": True}
 
 
 def rank_inputs(envs: int, rank: int):
@@ -249,7 +249,9 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
             "prep_us_per_launch": ms_prep * 1e3,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
+            # dram__bytes_read+write of conv_tc_kernel from profiles/r01_prof_conv_v4_summary.csv (B=32; that capture also
+            # reads the 33.5 MB residual; the operand and the output mostly stay in the 126 MB L2)
+            "traffic": 53.8e6, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
             "us_per_launch": ms * 1e3, "flop_per_launch": flops, "peak_source": peaks_src + " bf16 burst (fp16 and bf16 share the tensor-pipe rate)"}
 
 
@@ -290,10 +292,10 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    clk = ClockSampler(local); clk.start()  # samples clocks / throttle reasons from warm-up to the end of the timed regions
     for _ in range(max(args.warmup, 3)):
         sampler.sample(obs_d, act_d)
     barrier()
-    clk = ClockSampler(local); clk.start()
     lib.dmd_launch_count(1)
     evs = []
     t_wall0 = time.perf_counter()
@@ -342,7 +344,7 @@ def run_native(args):
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 activations", "data": "synthetic",
+            "dtype": "fp16 tensor-core operands (split-fp16 on the residual-stream 1x1/conv_in layers), fp32 accumulate, fp32 activations", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(obs_h.numel() * 4 + act_h.numel() * 8),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
