@@ -81,8 +81,24 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
     int n = 0;
     for (int rep = 0; rep < (d->precise ? 3 : 1); ++rep)  // [hi | lo | hi] against weights [W_hi | W_hi | W_lo]
       for (int k = 0; k < nsrc; ++k) { p->seg_base[n] = (rep == 1) ? lo[k] : hi[k]; p->seg_slabs[n] = cs[k] / 16; ++n; }
-    p->nseg = n;
     p->Cin = (d->C0 + d->C1) * (d->precise ? 3 : 1);
+    p->Cextra = 0;
+    if (d->wpk_x) {  // fused split-fp16 1x1 projection: [x_hi | x_lo | x_hi] against [W_hi | W_hi | W_lo], centre tap only
+      DMD_CHECK(d->xsrc0 && d->xsrc0_lo && d->xC0 > 0 && d->xC0 % 16 == 0 && d->xC1 % 16 == 0 && d->xC0 + d->xC1 <= kMaxCin, "conv: bad fused projection operands");
+      DMD_CHECK((d->xC1 == 0) == (d->xsrc1 == nullptr) && (d->xC1 == 0) == (d->xsrc1_lo == nullptr), "conv: fused projection src1 mismatch");
+      const uint8_t* xh[2] = {(const uint8_t*)d->xsrc0, (const uint8_t*)d->xsrc1};
+      const uint8_t* xl[2] = {(const uint8_t*)d->xsrc0_lo, (const uint8_t*)d->xsrc1_lo};
+      const int xc[2] = {d->xC0, d->xC1};
+      for (int rep = 0; rep < 3; ++rep)
+        for (int k = 0; k < (d->xC1 ? 2 : 1); ++k) {
+          DMD_CHECK(n < kMaxSegs, "conv: too many operand segments");
+          p->seg_base[n] = (rep == 1) ? xl[k] : xh[k]; p->seg_slabs[n] = xc[k] / 16; ++n;
+        }
+      p->Cextra = 3 * (d->xC0 + d->xC1);
+      p->wpk_extra = reinterpret_cast<const __half*>(d->wpk_x);
+      p->bias_extra = d->bias_x;
+    }
+    p->nseg = n;
   }
   p->B = d->B; p->H = d->H; p->W = d->W; p->taps = d->taps; p->stride = d->stride;
   if (d->stride == 2) DMD_CHECK(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H,W");
@@ -104,15 +120,16 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   p->dPW.init(g.PW); p->dPH.init(g.PH);
   p->num_tiles = (g.Q + kTileM - 1) / kTileM;
   // slab ring: everything that fits next to the resident weights, at most four tiles' worth
-  const int kslabs = p->Cin / 16;
-  const ConvSmemLayout L0 = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, 0);
+  const int kslabs = (p->Cin + p->Cextra) / 16;
+  const uint32_t w_bytes = conv_weight_bytes(p->taps, p->Cin, p->Cextra, p->CoutPad);
+  const ConvSmemLayout L0 = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, 0);
   const long long budget = 227ll * 1024 - (long long)L0.total;
   int stages = (int)(budget / (long long)L0.slab_bytes);
   if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
   DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
   p->stages = stages;
-  *smem = conv_smem_layout(p->taps, p->Cin, p->CoutPad, p->Palloc, stages).total;
+  *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages).total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
   return 0;
 }
@@ -469,8 +486,14 @@ struct PlanBuilder {
     return o;
   }
 
-  void conv(const ConvW& cw, const Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats) {
+  void conv(const ConvW& cw, const Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats,
+            const ConvW* xproj = nullptr, const Operand* xin = nullptr) {
     dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    if (xproj) {  // skip projection of the block input, accumulated into this conv's output tile
+      d.xsrc0 = xin->r0; d.xsrc0_lo = xin->rl0; d.xC0 = xin->C0;
+      if (xin->C1) { d.xsrc1 = xin->r1; d.xsrc1_lo = xin->rl1; d.xC1 = xin->C1; }
+      d.wpk_x = h->packed ? h->packed + xproj->pk_off : (const void*)1; d.bias_x = P(xproj->b_idx);
+    }
     d.src0 = raw ? in.r0 : in.n0; d.src1 = in.C1 ? (raw ? in.r1 : in.n1) : nullptr;
     d.precise = cw.precise;
     if (cw.precise) { d.src0_lo = raw ? in.rl0 : in.nl0; d.src1_lo = in.C1 ? in.rl1 : nullptr; }
@@ -490,14 +513,13 @@ struct PlanBuilder {
   Tens resblock(const ResBlockW& rb, const Tens& x, const Tens* skip) {
     const int H = x.H, W = x.W;
     Operand in1 = prep(x, skip, 0, 1, &rb.n1, 0, 0, true, rb.has_proj != 0, rb.has_proj != 0);
-    Tens r;
-    if (rb.has_proj) { r = tensor(rb.cout, H, W, false); conv(rb.proj, in1, true, 1, nullptr, r, false); }
-    else r = x;
     Tens t = tensor(rb.cout, H, W, true);
     conv(rb.c1, in1, false, 1, nullptr, t, true);
     Operand in2 = prep(t, nullptr, 0, 1, &rb.n2, 0, 0, true, false);
     Tens o = tensor(rb.cout, H, W, true);
-    conv(rb.c2, in2, false, 1, &r, o, true);
+    // x + r: r is the block input itself, or proj(input) fused into conv2's accumulator (no r tensor, no extra launch)
+    if (rb.has_proj) conv(rb.c2, in2, false, 1, nullptr, o, true, &rb.proj, &in1);
+    else conv(rb.c2, in2, false, 1, &x, o, true);
     if (!rb.has_attn) return o;
     Tens a = tensor(rb.cout, H, W, true);
     Op op; op.kind = OP_ATTN;

@@ -34,7 +34,7 @@ constexpr int kConvThreads = (2 + kEpiWarps) * 32;  // 320
 constexpr int kTileM = 128;
 constexpr int kMaxCin = 128;        // channels of one activation source
 constexpr int kMaxKChannels = 384;  // K extent per tap: up to 3 x 128 (split-fp16 "precise" convs)
-constexpr int kMaxSegs = 6;
+constexpr int kMaxSegs = 8;
 constexpr int kMaxStages = 24;
 constexpr int kStatSlots = 3;   // images a 128-row tile can touch
 constexpr int kMaxOutGroups = 4;
@@ -66,7 +66,11 @@ struct ConvParams {
   const uint8_t* seg_base[kMaxSegs];
   int seg_slabs[kMaxSegs];  // 16-channel slabs per segment
   int nseg;
-  int Cin;              // total K channels per tap
+  int Cin;              // K channels per tap of the main weights
+  int Cextra;           // trailing K channels that use ONLY the centre tap with their own weights: the fused 1x1 skip
+                        // projection r = proj(cat(x, skip)) accumulated into the same TMEM tile (blocks.py:133,142,145)
+  const __half* wpk_extra;  // [1][Cextra/8][CoutPad][8]
+  const float* bias_extra;  // [Cout] or null
   int B, H, W;          // conv input size
   int taps;             // 9 (3x3, pad 1) or 1 (1x1)
   int stride;           // 1 or 2 (stride 2 == stride-1 result sampled at even (y,x); exact for k=3,p=1)
@@ -92,7 +96,10 @@ struct ConvSmemLayout {
 };
 
 // barriers live in the first 512 bytes: wbar, full[24], empty[24], tfull[2], tempty[2], tmem slot
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, int CoutPad, int Palloc, int stages) {
+__host__ __device__ inline uint32_t conv_weight_bytes(int taps, int Cin, int Cextra, int CoutPad) {
+  return (((uint32_t)taps * Cin * CoutPad * 2 + 127u) & ~127u) + (uint32_t)Cextra * CoutPad * 2;
+}
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int CoutPad, int Palloc, int stages) {
   ConvSmemLayout L;
   L.bias_off = 512;
   L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
@@ -100,7 +107,6 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int taps, int Cin, in
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
   L.stage_off = (L.sstat_off + kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
   L.w_off = (L.stage_off + kTileM * L.stage_pitch + 127u) & ~127u;
-  const uint32_t w_bytes = (uint32_t)taps * Cin * CoutPad * 2;
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
   L.slab_bytes = 2u * Palloc * 16;
   L.total = L.a_off + (uint32_t)stages * L.slab_bytes + 16;
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   uint64_t* tfull = empty + kMaxStages;      // [2]
   uint64_t* tempty = tfull + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const ConvSmemLayout L = conv_smem_layout(p.taps, p.Cin, p.CoutPad, p.Palloc, p.stages);
+  const ConvSmemLayout L = conv_smem_layout(conv_weight_bytes(p.taps, p.Cin, p.Cextra, p.CoutPad), p.CoutPad, p.Palloc, p.stages);
   float* sbias = reinterpret_cast<float*>(smem + L.bias_off);
   int2* rowinfo = reinterpret_cast<int2*>(smem + L.rowinfo_off);
   float* sstat = reinterpret_cast<float*>(smem + L.sstat_off);
@@ -135,7 +141,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   const int warp = tid >> 5, lane = tid & 31;
   const int halo = (p.taps == 9) ? (p.PW + 1) : 0;
   const int S = p.stages;
-  const int kslabs = p.Cin >> 4;
+  const int main_slabs = p.Cin >> 4;
+  const int kslabs = main_slabs + (p.Cextra >> 4);
+  const uint32_t w_main_bytes = ((uint32_t)p.taps * p.Cin * p.CoutPad * 2 + 127u) & ~127u;
   // contiguous, balanced tile range per CTA: neighbouring tiles share halo rows (L2 hits)
   const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
@@ -149,12 +157,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
-    mbar_expect_tx(wbar, tap_bytes * p.taps);
+    const uint32_t extra_bytes = (uint32_t)p.Cextra * p.CoutPad * 2;
+    mbar_expect_tx(wbar, tap_bytes * p.taps + extra_bytes);
     for (int t = 0; t < p.taps; ++t)
       bulk_g2s(sW + (size_t)t * tap_bytes, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)t * tap_bytes, tap_bytes, wbar);
+    if (extra_bytes) bulk_g2s(sW + w_main_bytes, p.wpk_extra, extra_bytes, wbar);
   }
   if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_slot);
-  for (int i = tid; i < 128; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  for (int i = tid; i < 128; i += blockDim.x)
+    sbias[i] = ((p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f) + ((p.bias_extra != nullptr && i < p.Cout) ? __ldg(p.bias_extra + i) : 0.f);
   for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
@@ -198,6 +209,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
       const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
       const uint32_t b_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_x0 = (((smem_u32(sW) + w_main_bytes) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
       const uint32_t slab16 = L.slab_bytes >> 4;
       const uint32_t tap16 = ((uint32_t)p.Cin * p.CoutPad * 2) >> 4;     // bytes of one tap of weights, /16
       const uint32_t kstep16 = (2u * b_lbo) >> 4;                          // one 16-channel slab of weights, /16
@@ -224,7 +236,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           DMD_TS(1, it, (ks & 3) * 3 + 1);
           tc_fence_after_sync();
           if (!(p.dbg & 2)) {
-            if (p.taps == 9) {
+            if (ks >= main_slabs) {
+              // fused projection: centre tap only, its own weight block
+              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)halo);
+              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
+              umma_f16(d_tmem, ad, bd, idesc, 1u);
+            } else if (p.taps == 9) {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
                 const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);

@@ -96,7 +96,7 @@ def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h
                    cout_pad: int, taps: int = 9, *, bias: Optional[Tensor] = None, stride: int = 1,
                    residual: Optional[Tensor] = None, out_gs: int = 0, out: Optional[Tensor] = None,
                    ostats: Optional[Tensor] = None, debug: int = 0, debug_buf: Optional[Tensor] = None,
-                   lo0: Optional[Tensor] = None, lo1: Optional[Tensor] = None):
+                   lo0: Optional[Tensor] = None, lo1: Optional[Tensor] = None, xproj=None):
     """tcgen05 conv on already prepared PLC16 operand(s) (one kernel launch)."""
     _cuda(n0, n1, wpk, bias, residual)
     ho, wo = h // stride, w // stride
@@ -111,6 +111,10 @@ def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h
     d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
     d.debug_buf = _lib.ptr(debug_buf)
     d.precise, d.src0_lo, d.src1_lo = int(lo0 is not None), _lib.ptr(lo0), _lib.ptr(lo1)
+    if xproj is not None:  # fused split-fp16 1x1 projection: (hi0, hi1, lo0, lo1, C0, C1, wpk_x, bias_x)
+        xh0, xh1, xl0, xl1, xc0, xc1, wpk_x, bias_x = xproj
+        d.xsrc0, d.xsrc1, d.xsrc0_lo, d.xsrc1_lo = xh0.data_ptr(), _lib.ptr(xh1), xl0.data_ptr(), _lib.ptr(xl1)
+        d.xC0, d.xC1, d.wpk_x, d.bias_x = xc0, xc1, wpk_x.data_ptr(), _lib.ptr(bias_x)
     _lib.check(_lib.lib().dmd_conv2d_fprop(C.byref(d), _lib.current_stream()))
     return out, ostats
 

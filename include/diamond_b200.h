@@ -94,6 +94,13 @@ typedef struct dmd_conv_desc {
   int precise;           /* 1: split-fp16 (needs src*_lo and weights packed with precise = 1) */
   const void* src0_lo;
   const void* src1_lo;
+  /* Optional fused 1x1 projection accumulated into the same output: out += W_x . cat(x0, x1) + b_x  (the skip path
+   * r = proj(x) of ResBlock.forward, blocks.py:142,145).  Operands are split-fp16 (hi + lo), weights packed with taps = 1,
+   * precise = 1. */
+  const void* xsrc0; const void* xsrc1; const void* xsrc0_lo; const void* xsrc1_lo;
+  int xC0, xC1;
+  const void* wpk_x;
+  const float* bias_x;
 } dmd_conv_desc;
 
 int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);

@@ -33,5 +33,5 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_sizes_match_header_layout():
     # natural alignment, 64-bit pointers: guards against field drift between the header and the ctypes mirror
     assert ctypes.sizeof(_lib.DenoiserConfigC) == 4 * 4 + 3 * 8 * 4 + 4 + 2 * 4
-    assert ctypes.sizeof(_lib.ConvDesc) == 136 and ctypes.sizeof(_lib.PrepDesc) == 176
+    assert ctypes.sizeof(_lib.ConvDesc) == 192 and ctypes.sizeof(_lib.PrepDesc) == 176
     assert ctypes.sizeof(_lib.SamplerConfigC) == 40

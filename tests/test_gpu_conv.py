@@ -137,6 +137,31 @@ def test_conv_precise_split_fp16(case):
     assert _rel(got, ref32) < 5e-6, _rel(got, ref32)
 
 
+def test_conv_with_fused_skip_projection():
+    """ResBlock tail (blocks.py:142-145): conv2(silu(norm2(t))) + proj(cat(x, skip)) in ONE launch — the 1x1 projection is
+    extra K (split-fp16, centre tap) accumulated into the same TMEM tile."""
+    dev = _dev()
+    from diamond_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    b, h, w = 3, 32, 32
+    t = torch.randn(b, 64, h, w, generator=g)
+    x, sk = torch.randn(b, 64, h, w, generator=g) * 2, torch.randn(b, 64, h, w, generator=g) + 0.5
+    w2 = torch.randn(64, 64, 3, 3, generator=g) / 24; b2 = torch.randn(64, generator=g) * 0.1
+    wp = torch.randn(64, 128, 1, 1, generator=g) / 11; bp = torch.randn(64, generator=g) * 0.1
+    ref = F.conv2d(_h(t).double(), _h(w2).double(), b2.double(), padding=1).float() + F.conv2d(torch.cat([x, sk], 1), wp, bp)
+    tn, xn, sn = (ops.nchw_to_nhwc(v.to(dev)) for v in (t, x, sk))
+    n0 = ops.prep_act(tn)[0]
+    res = ops.prep_act(xn, src1=sn, also_raw=False, split=True)  # raw mode: main operand = raw hi, lo parts via split
+    xh0, xh1, xl0, xl1 = res[0], res[1], res[6], res[7]
+    wpk2, cp = ops.pack_conv_weight(w2.to(dev), 64)
+    wpkx, _ = ops.pack_conv_weight(wp.to(dev), 128, precise=True)
+    out, _ = ops.conv2d_operand(n0, None, 64, 0, b, h, w, wpk2, 64, cp, bias=b2.to(dev),
+                                xproj=(xh0, xh1, xl0, xl1, 64, 64, wpkx, bp.to(dev)))
+    got = ops.nhwc_to_nchw(out).cpu()
+    assert _rel(got, ref) < 2e-5, _rel(got, ref)
+
+
 def test_conv_linearity_and_zero():
     """size-independent properties: conv(0)=bias, conv(a+b)-bias = (conv(a)-bias)+(conv(b)-bias) up to fp16 rounding."""
     dev = _dev()
