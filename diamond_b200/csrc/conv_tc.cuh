@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (et == 0) DMD_TS(2, it, 2);
       // ---- pass 2: staging -> (+residual) -> coalesced global stores, GroupNorm partial sums
       if (vec_ok) {
-        float s[kStatSlots] = {0.f, 0.f, 0.f}, ss[kStatSlots] = {0.f, 0.f, 0.f};
+        // scalar accumulators (arrays indexed by the image slot end up in local memory)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss0 = 0.f, ss1 = 0.f, ss2 = 0.f;
         // L4 is a power of two (host-checked for the vector path): thread owns channel quad c4 of rows r0, r0+rstep, ...
 #pragma unroll
         for (int k0 = 0; k0 < 16; k0 += 4) {
@@ -373,13 +374,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
                 if (p.ostats != nullptr) {
                   const float ps = (o.x + o.y) + (o.z + o.w);
                   const float pss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                  if (single_image) { s[0] += ps; ss[0] += pss; }
-                  else {
-#pragma unroll
-                    for (int k = 0; k < kStatSlots; ++k) {
-                      if (ri[u].y == k) { s[k] += ps; ss[k] += pss; }
-                    }
-                  }
+                  const int sl = ri[u].y;   // 0 on single-image tiles
+                  s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
+                  s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
+                  s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
                 }
               }
             }
@@ -390,32 +388,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           const int ogrp = (c4 * 4) / p.ogs;
           const int lanes_per_group = p.ogs >> 2;   // lanes (float4s) covering one group inside a row
           // most tiles touch one image: skip the reductions of unused image slots (warp-uniform test)
-          bool used[kStatSlots];
-#pragma unroll
-          for (int k = 0; k < kStatSlots; ++k) used[k] = (k == 0) ? true : (!single_image && __any_sync(0xffffffffu, ss[k] != 0.f));
+          const bool multi = !single_image;   // warp-uniform: most tiles touch one image, skip the other slots
           bool leader = true;
 #pragma unroll
           for (int m = 1; m < 32; m <<= 1) {
             // the xor-m partner lane is in the same group iff m stays inside the group span or jumps whole rows
             const bool same = (m < lanes_per_group && m < L4) || (m >= L4);
             if (same) {
-#pragma unroll
-              for (int k = 0; k < kStatSlots; ++k) {
-                if (used[k]) {
-                  s[k] += __shfl_xor_sync(0xffffffffu, s[k], m);
-                  ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], m);
-                }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+              ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+              if (multi) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+                ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+                ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
               }
               if (lane & m) leader = false;
             }
           }
           if (leader) {  // exactly one leader lane per (warp, group): plain stores, summed in fixed order below
-#pragma unroll
-            for (int k = 0; k < kStatSlots; ++k) {
-              float* dstp = sstat + (((size_t)ew * kStatSlots + k) * kMaxOutGroups + ogrp) * 2;
-              dstp[0] = s[k];
-              dstp[1] = ss[k];
-            }
+            float* dstp = sstat + ((size_t)ew * kStatSlots * kMaxOutGroups + ogrp) * 2;
+            *reinterpret_cast<float2*>(dstp) = make_float2(s0, ss0);
+            *reinterpret_cast<float2*>(dstp + kMaxOutGroups * 2) = make_float2(s1, ss1);
+            *reinterpret_cast<float2*>(dstp + 2 * kMaxOutGroups * 2) = make_float2(s2, ss2);
           }
         }
       } else {
@@ -436,9 +431,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (p.ostats != nullptr && et < kStatSlots * G * 2) {
         const int k = et / (G * 2), r = et - k * (G * 2);
         const int ogrp = r >> 1, which = r & 1;
-        double val = 0.0;
+        float pw[kEpiWarps];
 #pragma unroll
-        for (int w = 0; w < kEpiWarps; ++w) val += (double)sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + ogrp) * 2 + which];
+        for (int w = 0; w < kEpiWarps; ++w) pw[w] = sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + ogrp) * 2 + which];
+        // fixed-order pairwise tree: deterministic, three dependent adds instead of eight fp64 ones
+        const double val = (double)(((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7])));
         const int img = n_lo + k;
         if (val != 0.0 && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + ogrp) * 2 + which, val);
       }
