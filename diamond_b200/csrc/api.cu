@@ -146,7 +146,9 @@ static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (nev
   DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   done = true;
   return 0;
 }
@@ -206,7 +208,11 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   p->gamma = d->gamma; p->beta = d->beta; p->eps = d->eps;
   const Plc g = plc_geometry(d->B, p->H, p->W);
   DMD_CHECK(g.PH * g.PW >= 32, "prep: image too small");
-  p->pos_per_block = g.PH * g.PW >= 256 ? 256 : (g.PH * g.PW / 32) * 32;  // a block touches at most 2 images
+  // a block touches at most 2 images; low-resolution levels get smaller blocks so that the grid still covers the SMs
+  int ppb = g.PH * g.PW >= 256 ? 256 : (g.PH * g.PW / 32) * 32;
+  while (ppb > 64 && (g.Qalloc + ppb - 1) / ppb < 2 * 148) ppb >>= 1;
+  ppb = (ppb / 32) * 32;
+  p->pos_per_block = ppb;
   DMD_CHECK(d->C0 / (d->gs0 > 0 ? d->gs0 : 8) <= 4 || d->mode == 0, "prep: at most 4 groups per source");
   DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "prep: problem too large for 32-bit position math");
   p->PW = g.PW; p->PH = g.PH; p->Q = g.Q; p->G = g.G; p->Qalloc = g.Qalloc; p->plane_bytes = (unsigned long long)g.Qalloc * 16;
@@ -273,7 +279,14 @@ static int linear_launch(const float* in, const float* W, const float* bias, flo
   DMD_CHECK(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
   DMD_CHECK(hw_perm == 0 || K % hw_perm == 0, "linear: bad hw_perm");
   if (init_kernels()) return 1;
-  linear_kernel<<<dim3((F + 31) / 32, (B + 31) / 32), 256, (size_t)64 * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
+  // enough blocks to cover the SMs: 8, 16 or 32 output features per block
+  const int by = (B + 31) / 32;
+  if ((long long)((F + 31) / 32) * by >= 296)
+    linear_kernel<4><<<dim3((F + 31) / 32, by), 256, (size_t)(32 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
+  else if ((long long)((F + 15) / 16) * by >= 148)
+    linear_kernel<2><<<dim3((F + 15) / 16, by), 256, (size_t)(16 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
+  else
+    linear_kernel<1><<<dim3((F + 7) / 8, by), 256, (size_t)(8 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
   DMD_LAUNCH_OK();
   return 0;
 }

@@ -85,24 +85,29 @@ __global__ void cond_embed_kernel(const float* __restrict__ cs, const int64_t* _
 }
 
 // out[n][f] (+)= act( sum_k in[n][k] * W[f][k] + b[f] ),  K multiple of 4; K is processed in chunks of <= 256.
-// grid (ceil(F/32), ceil(B/32)), 256 threads: warp w owns rows f = 4w..4w+3 of the 32-row tile, lane = sample n.
+// grid (ceil(F/(8J)), ceil(B/32)), 256 threads: warp w owns rows f = Jw..Jw+J-1 of the 8J-row tile, lane = sample n.
+// J = 1 gives small GEMMs (the conditioning MLP: F = 256) four times the blocks; the k order of each sum is the same.
 // hw_perm > 0: `in` is an NHWC tensor [B][hw_perm][K/hw_perm] read in NCHW-flatten order (k = c*hw + pix), i.e. the
 // x.flatten(start_dim=1) of actor_critic.py:71 without materialising the permutation.
 constexpr int kLinChunk = 256;
+template <int J>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                      const float* __restrict__ bias, float* __restrict__ out, int B,
                                                      int K, int F, int silu, int accumulate, int hw_perm) {
   extern __shared__ __align__(16) float sm_lin[];
-  float* Ws = sm_lin;                    // [32][kLinChunk]
-  float* inT = sm_lin + 32 * kLinChunk;  // [kLinChunk][32]
-  const int f0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  constexpr int FT = 8 * J;              // output features per block
+  float* Ws = sm_lin;                    // [FT][kLinChunk]
+  float* inT = sm_lin + FT * kLinChunk;  // [kLinChunk][32]
+  const int f0 = blockIdx.x * FT, n0 = blockIdx.y * 32;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) acc[j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kLinChunk) {
     const int kc = min(kLinChunk, K - k0), kc4 = kc >> 2;
     __syncthreads();
-    for (int i = tid; i < 32 * kc4; i += 256) {
+    for (int i = tid; i < FT * kc4; i += 256) {
       const int r = i / kc4, c4 = i - r * kc4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f0 + r < F) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(f0 + r) * K + k0) + c4);
@@ -123,8 +128,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
       const float x0 = inT[(4 * k4 + 0) * 32 + lane], x1 = inT[(4 * k4 + 1) * 32 + lane];
       const float x2 = inT[(4 * k4 + 2) * 32 + lane], x3 = inT[(4 * k4 + 3) * 32 + lane];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = reinterpret_cast<const float4*>(Ws + (warp * 4 + j) * kLinChunk)[k4];
+      for (int j = 0; j < J; ++j) {
+        const float4 w = reinterpret_cast<const float4*>(Ws + (warp * J + j) * kLinChunk)[k4];
         acc[j] = fmaf(w.x, x0, acc[j]); acc[j] = fmaf(w.y, x1, acc[j]);
         acc[j] = fmaf(w.z, x2, acc[j]); acc[j] = fmaf(w.w, x3, acc[j]);
       }
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
   }
   if (n0 + lane < B) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int f = f0 + warp * 4 + j;
+    for (int j = 0; j < J; ++j) {
+      const int f = f0 + warp * J + j;
       if (f < F) {
         float v = acc[j] + (bias ? bias[f] : 0.f);
         float* o = out + (size_t)(n0 + lane) * F + f;

@@ -277,12 +277,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     const int G = p.ostats ? p.Cout / p.ogs : 1;
     const int L4 = p.Cout >> 2;                // float4 per output row (vector path)
     const bool vec_ok = (p.Cout & 3) == 0 && (L4 & (L4 - 1)) == 0 && L4 <= 32;  // 16/32/64/128 channels
+    const int lg = 31 - __clz(L4 > 0 ? L4 : 1);
+    const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
+    const int ogrp = p.ostats ? (c4 * 4) / p.ogs : 0;   // a thread's channel quad, hence its group, is fixed
+    const int lanes_per_group = p.ogs >> 2;            // lanes (float4s) covering one group inside a row
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       const int q0 = (tile_begin + it) * kTileM;
       const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
       const int q_last = min(q0 + kTileM, p.Q) - 1;
       const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;  // all rows of the tile in one image
+      if (et == 0) DMD_TS(2, it, 7);
       // ---- row bookkeeping (one thread per row)
       if (et < kTileM) {
         const int q = q0 + et;
@@ -303,8 +308,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         rowinfo[et] = make_int2(opix, slot);
       }
       // ---- residual prefetch: it does not depend on the accumulator, so its latency hides behind the MMAs of this tile
-      const int lg = 31 - __clz(L4 > 0 ? L4 : 1);
-      const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
       const int iters = vec_ok ? kTileM / rstep : 0;  // 2..16
       float4 rpre[8];
       const bool prefetch = vec_ok && p.resid != nullptr && iters <= 8;
@@ -383,10 +386,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             }
           }
         }
+        if (et == 0) DMD_TS(2, it, 4);
         if (p.ostats != nullptr) {
           // host guarantees L4 in {4, 8, 16, 32} (so 256 % L4 == 0): a thread's channel quad, hence its group, is fixed
-          const int ogrp = (c4 * 4) / p.ogs;
-          const int lanes_per_group = p.ogs >> 2;   // lanes (float4s) covering one group inside a row
           // most tiles touch one image: skip the reductions of unused image slots (warp-uniform test)
           const bool multi = !single_image;   // warp-uniform: most tiles touch one image, skip the other slots
           bool leader = true;
@@ -427,7 +429,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           }
         }
       }
+      if (et == 0) DMD_TS(2, it, 5);
       named_bar_sync(9, kEpiThreads);   // staging / rowinfo may be reused; sstat complete
+      if (et == 0) DMD_TS(2, it, 6);
       if (p.ostats != nullptr && et < kStatSlots * G * 2) {
         const int k = et / (G * 2), r = et - k * (G * 2);
         const int ogrp = r >> 1, which = r & 1;

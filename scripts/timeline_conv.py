@@ -38,4 +38,6 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid"
     b = buf.cpu().view(3, 16, 16).double()
     p1 = (b[2, 1:6, 2] - b[2, 1:6, 1]).mean(); p2 = (b[2, 1:6, 3] - b[2, 1:6, 2]).mean()
     mma = (b[1, 1:6, 14] - b[1, 1:6, 13]).mean(); tile = (b[2, 2:6, 3] - b[2, 1:5, 3]).mean()
-    print(f"{name:18s} pass1={p1:7.0f} pass2={p2:7.0f} mma_tile={mma:7.0f} tile_period={tile:7.0f}")
+    seg = lambda a, c: float((b[2, 1:6, a] - b[2, 1:6, c]).mean())
+    print(f"{name:18s} pass1={p1:7.0f} pass2={p2:7.0f} mma_tile={mma:7.0f} tile_period={tile:7.0f} | top->wait {seg(0, 7):6.0f} wait {seg(1, 0):6.0f} "
+          f"loop {seg(4, 2):6.0f} shfl {seg(5, 4):6.0f} bar9 {seg(6, 5):6.0f} flush {seg(3, 6):6.0f}")
