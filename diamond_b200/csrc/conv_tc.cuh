@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
     if (lane == 0 && my_tiles > 0) {
       mbar_wait(wbar, 0);
-      const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(kTileM, (p.dbg & 64) ? 32u : (uint32_t)p.CoutPad, 0, 0);  // dbg 64: timing experiment, N = 32
       const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
       const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
       const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         shift[t] = (uint32_t)(halo + ((p.taps == 9) ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
+        if (p.dbg & 16) shift[t] = 0;                            // timing experiment: every tap reads the 128-byte aligned slab base
+        if (p.dbg & 32) shift[t] = (uint32_t)(8 * t);            // timing experiment: aligned but distinct addresses
         b_tap[t] = (uint32_t)t * tap16;
       }
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
@@ -281,6 +283,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
     const int ogrp = p.ostats ? (c4 * 4) / p.ogs : 0;   // a thread's channel quad, hence its group, is fixed
     const int lanes_per_group = p.ogs >> 2;            // lanes (float4s) covering one group inside a row
+    // GroupNorm partial sums (scalars: arrays indexed by the image slot end up in local memory).  A CTA owns a contiguous
+    // range of tiles and an image spans many tiles, so (s0, ss0) RUN across consecutive single-image tiles of image n_cur and
+    // are reduced / flushed only when the image changes; a tile that straddles images uses the three slots and flushes at once.
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss0 = 0.f, ss1 = 0.f, ss2 = 0.f;
+    int n_cur = -1;
+    auto flush_stats = [&](int img0, bool multi) {
+      bool leader = true;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        // the xor-m partner lane is in the same group iff m stays inside the group span or jumps whole rows
+        const bool same = (m < lanes_per_group && m < L4) || (m >= L4);
+        if (same) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+          if (multi) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+            ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+            ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
+          }
+          if (lane & m) leader = false;
+        }
+      }
+      if (leader) {  // exactly one leader lane per (warp, group): plain stores, summed in fixed order below
+        float* dstp = sstat + ((size_t)ew * kStatSlots * kMaxOutGroups + ogrp) * 2;
+        *reinterpret_cast<float2*>(dstp) = make_float2(s0, ss0);
+        if (multi) {
+          *reinterpret_cast<float2*>(dstp + kMaxOutGroups * 2) = make_float2(s1, ss1);
+          *reinterpret_cast<float2*>(dstp + 2 * kMaxOutGroups * 2) = make_float2(s2, ss2);
+        }
+      }
+      named_bar_sync(11, kEpiThreads);   // every reuse of sstat is separated from these reads by barrier 8 or 9
+      if (et < (multi ? kStatSlots : 1) * G * 2) {
+        const int k = et / (G * 2), r = et - k * (G * 2);
+        const int og = r >> 1, which = r & 1;
+        float pw[kEpiWarps];
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) pw[w] = sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + og) * 2 + which];
+        // fixed-order pairwise tree: deterministic within the CTA
+        const double val = (double)(((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7])));
+        const int img = img0 + k;
+        if (val != 0.0 && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + og) * 2 + which, val);
+      }
+      s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       const int q0 = (tile_begin + it) * kTileM;
@@ -288,6 +335,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       const int q_last = min(q0 + kTileM, p.Q) - 1;
       const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;  // all rows of the tile in one image
       if (et == 0) DMD_TS(2, it, 7);
+      if (n_cur >= 0 && (!single_image || n_lo != n_cur)) { flush_stats(n_cur, false); n_cur = -1; }
       // ---- row bookkeeping (one thread per row)
       if (et < kTileM) {
         const int q = q0 + et;
@@ -350,8 +398,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (et == 0) DMD_TS(2, it, 2);
       // ---- pass 2: staging -> (+residual) -> coalesced global stores, GroupNorm partial sums
       if (vec_ok) {
-        // scalar accumulators (arrays indexed by the image slot end up in local memory)
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss0 = 0.f, ss1 = 0.f, ss2 = 0.f;
         // L4 is a power of two (host-checked for the vector path): thread owns channel quad c4 of rows r0, r0+rstep, ...
 #pragma unroll
         for (int k0 = 0; k0 < 16; k0 += 4) {
@@ -377,10 +423,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
                 if (p.ostats != nullptr) {
                   const float ps = (o.x + o.y) + (o.z + o.w);
                   const float pss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                  const int sl = ri[u].y;   // 0 on single-image tiles
-                  s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
-                  s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
-                  s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
+                  if (single_image) { s0 += ps; ss0 += pss; }
+                  else {
+                    const int sl = ri[u].y;
+                    s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
+                    s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
+                    s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
+                  }
                 }
               }
             }
@@ -388,32 +437,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         }
         if (et == 0) DMD_TS(2, it, 4);
         if (p.ostats != nullptr) {
-          // host guarantees L4 in {4, 8, 16, 32} (so 256 % L4 == 0): a thread's channel quad, hence its group, is fixed
-          // most tiles touch one image: skip the reductions of unused image slots (warp-uniform test)
-          const bool multi = !single_image;   // warp-uniform: most tiles touch one image, skip the other slots
-          bool leader = true;
-#pragma unroll
-          for (int m = 1; m < 32; m <<= 1) {
-            // the xor-m partner lane is in the same group iff m stays inside the group span or jumps whole rows
-            const bool same = (m < lanes_per_group && m < L4) || (m >= L4);
-            if (same) {
-              s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-              ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
-              if (multi) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-                ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-                ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
-              }
-              if (lane & m) leader = false;
-            }
-          }
-          if (leader) {  // exactly one leader lane per (warp, group): plain stores, summed in fixed order below
-            float* dstp = sstat + ((size_t)ew * kStatSlots * kMaxOutGroups + ogrp) * 2;
-            *reinterpret_cast<float2*>(dstp) = make_float2(s0, ss0);
-            *reinterpret_cast<float2*>(dstp + kMaxOutGroups * 2) = make_float2(s1, ss1);
-            *reinterpret_cast<float2*>(dstp + 2 * kMaxOutGroups * 2) = make_float2(s2, ss2);
-          }
+          if (single_image) n_cur = n_lo;            // keep running
+          else { flush_stats(n_lo, true); n_cur = -1; }
         }
       } else {
         // narrow outputs (conv_out: 3 channels): scalar stores, no statistics
@@ -432,19 +457,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (et == 0) DMD_TS(2, it, 5);
       named_bar_sync(9, kEpiThreads);   // staging / rowinfo may be reused; sstat complete
       if (et == 0) DMD_TS(2, it, 6);
-      if (p.ostats != nullptr && et < kStatSlots * G * 2) {
-        const int k = et / (G * 2), r = et - k * (G * 2);
-        const int ogrp = r >> 1, which = r & 1;
-        float pw[kEpiWarps];
-#pragma unroll
-        for (int w = 0; w < kEpiWarps; ++w) pw[w] = sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + ogrp) * 2 + which];
-        // fixed-order pairwise tree: deterministic, three dependent adds instead of eight fp64 ones
-        const double val = (double)(((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7])));
-        const int img = n_lo + k;
-        if (val != 0.0 && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + ogrp) * 2 + which, val);
-      }
       if (et == 0) DMD_TS(2, it, 3);
     }
+    if (n_cur >= 0) flush_stats(n_cur, false);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -29,7 +29,9 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("stats+
 
 print("==== summary (cycles, mean over tiles 1..5 of CTA 0)")
 for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid", dict(out_gs=0, residual=x)), ("stats+resid", dict(out_gs=32, residual=x)),
-                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8))):
+                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("shift0(dbg16)", dict(out_gs=0, debug=8 | 16)),
+                 ("aligned(dbg32)", dict(out_gs=0, debug=8 | 32)), ("N32(dbg64)", dict(out_gs=0, debug=8 | 64)),
+                 ("N32+shift0", dict(out_gs=0, debug=8 | 16 | 64))):
     buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device=dev)
     for rep in range(2):
         buf.zero_()
