@@ -117,8 +117,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Bring-up instrumentation (clock64 role timeline, "skip" switches) exists only in -DDMD_TIMELINE builds: the producer and
+// MMA warps are latency-bound on their own scalar instructions, so even a not-taken debug test per slab is measurable.
+#ifdef DMD_TIMELINE
+#define DMD_DBG(bit) (p.dbg & (bit))
 #define DMD_TS(role, it_, ev) \
   do { if (p.dbg_buf && blockIdx.x == 0 && (it_) < 16) p.dbg_buf[((role) * 16 + (it_)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define DMD_DBG(bit) 0
+#define DMD_TS(role, it_, ev) do { } while (0)
+#endif
 
 template <int kAccCols>  // TMEM columns per accumulator (>= CoutPad); two accumulators are allocated
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvParams p) {
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
 
   if (warp == 0) {
     // =========================================================================================== PRODUCER (TMA)
-    if (lane == 0) {
+    {  // converged warp, one elected lane issues the copies (uniform-register operands)
       const uint32_t chunk_bytes = (uint32_t)p.P * 16;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -186,11 +194,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           DMD_TS(0, it, (ks & 3) * 3 + 0);
           mbar_wait(empty + stage, phase ^ 1u);
           DMD_TS(0, it, (ks & 3) * 3 + 1);
-          uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
-          mbar_expect_tx(full + stage, 2 * chunk_bytes);
-          const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
-          bulk_g2s(slab, plane, chunk_bytes, full + stage);
-          bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+          if (elect_one_sync()) {
+            uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
+            mbar_expect_tx(full + stage, 2 * chunk_bytes);
+            const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
+            bulk_g2s(slab, plane, chunk_bytes, full + stage);
+            bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+          }
+          __syncwarp();
           DMD_TS(0, it, (ks & 3) * 3 + 2);
           if (++seg_ks == p.seg_slabs[seg]) { seg_ks = 0; ++seg; }
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
@@ -200,11 +211,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     __syncwarp();
   } else if (warp == 1) {
     // =========================================================================================== MMA ISSUER
-    // One thread.  Descriptor words are precomputed: per MMA only the 14-bit start-address fields change
-    // (A: ring stage + tap shift, both in 16-byte units; B: tap + slab), so the issue loop is ~6 instructions per MMA.
-    if (lane == 0 && my_tiles > 0) {
+    // The whole warp walks the loop CONVERGED and one elected lane issues (elect.sync): every loop variable is warp-uniform,
+    // so the descriptors live in uniform registers and each tcgen05.mma is a single predicated UTCHMMA.  (Issuing from a
+    // divergent `lane == 0` branch makes ptxas wrap every MMA in an R2UR + ELECT uniformisation loop; the issuing thread is
+    // latency-bound on its own scalar instructions, so that overhead -- not the tensor pipe -- set the tile time.)
+    // Descriptor words are precomputed: per MMA only the 14-bit start-address fields change (A: ring stage + tap shift,
+    // both in 16-byte units; B: tap + slab).
+    if (my_tiles > 0) {
       mbar_wait(wbar, 0);
-      const uint32_t idesc = umma_idesc_f16(kTileM, (p.dbg & 64) ? 32u : (uint32_t)p.CoutPad, 0, 0);  // dbg 64: timing experiment, N = 32
+      const uint32_t idesc = umma_idesc_f16(kTileM, (uint32_t)p.CoutPad, 0, 0);
       const uint32_t a_lbo = (uint32_t)p.Palloc * 16, b_lbo = (uint32_t)p.CoutPad * 16;
       const uint32_t hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
       const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
@@ -213,12 +228,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       const uint32_t slab16 = L.slab_bytes >> 4;
       const uint32_t tap16 = ((uint32_t)p.Cin * p.CoutPad * 2) >> 4;     // bytes of one tap of weights, /16
       const uint32_t kstep16 = (2u * b_lbo) >> 4;                          // one 16-channel slab of weights, /16
+      const bool nine = p.taps == 9;
       uint32_t shift[9], b_tap[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        shift[t] = (uint32_t)(halo + ((p.taps == 9) ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
-        if (p.dbg & 16) shift[t] = 0;                            // timing experiment: every tap reads the 128-byte aligned slab base
-        if (p.dbg & 32) shift[t] = (uint32_t)(8 * t);            // timing experiment: aligned but distinct addresses
+        shift[t] = (uint32_t)(halo + (nine ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
         b_tap[t] = (uint32_t)t * tap16;
       }
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
@@ -237,32 +251,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           mbar_wait(full + stage, phase);
           DMD_TS(1, it, (ks & 3) * 3 + 1);
           tc_fence_after_sync();
-          if (!(p.dbg & 2)) {
-            if (ks >= main_slabs) {
-              // fused projection: centre tap only, its own weight block
-              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)halo);
-              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
-              umma_f16(d_tmem, ad, bd, idesc, 1u);
-            } else if (p.taps == 9) {
+          if (elect_one_sync()) {
+            if (!DMD_DBG(2)) {
+              if (ks >= main_slabs) {
+                // fused projection: centre tap only, its own weight block
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)halo);
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
+                umma_f16(d_tmem, ad, bd, idesc, 1u);
+              } else if (nine) {
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
-                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + b_tap[t]);
-                umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
+                for (int t = 0; t < 9; ++t) {
+                  const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
+                  const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + b_tap[t]);
+                  umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
+                }
+              } else {
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[0]);
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)b_lo;
+                umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
               }
-            } else {
-              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[0]);
-              const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)b_lo;
-              umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
             }
+            umma_commit(empty + stage);                       // slab reusable once these MMAs retire
+            if (ks == kslabs - 1) umma_commit(tfull + b);     // accumulator complete (same lane: commits track its MMAs)
           }
-          umma_commit(empty + stage);  // slab reusable once these MMAs retire
+          __syncwarp();
           DMD_TS(1, it, (ks & 3) * 3 + 2);
           b_lo += kstep16;
           a_lo += slab16;
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
         }
-        umma_commit(tfull + b);        // accumulator complete
         DMD_TS(1, it, 14);
       }
     }
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
             yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
           }
-          if (valid && !(p.dbg & 8)) { opix = (n * Ho + yo) * Wo + xo; slot = n - n_lo; }
+          if (valid && !DMD_DBG(8)) { opix = (n * Ho + yo) * Wo + xo; slot = n - n_lo; }
         }
         rowinfo[et] = make_int2(opix, slot);
       }

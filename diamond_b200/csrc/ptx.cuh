@@ -142,6 +142,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start
 // its prologue now.  wait: block until the previous kernel has completed and its memory is visible.
+// elect.sync: one lane of a CONVERGED warp (deterministic for a given mask).  Code under `if (elect_one_sync())` keeps
+// warp-uniform values in uniform registers, which is what tcgen05.mma / cp.async.bulk / tcgen05.commit want.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

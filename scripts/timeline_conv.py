@@ -1,4 +1,8 @@
-"""GPU: clock64 timeline of CTA 0's roles for one conv launch (bring-up instrumentation)."""
+"""GPU: clock64 timeline of CTA 0's roles for one conv launch (bring-up instrumentation).
+
+Needs a library built with the instrumentation compiled in:  DMD_EXTRA=-DDMD_TIMELINE bash diamond_b200/csrc/build.sh
+(the production build compiles it out: the MMA / producer warps are latency-bound on their scalar instructions).
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -29,9 +33,10 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("stats+
 
 print("==== summary (cycles, mean over tiles 1..5 of CTA 0)")
 for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid", dict(out_gs=0, residual=x)), ("stats+resid", dict(out_gs=32, residual=x)),
-                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("shift0(dbg16)", dict(out_gs=0, debug=8 | 16)),
-                 ("aligned(dbg32)", dict(out_gs=0, debug=8 | 32)), ("N32(dbg64)", dict(out_gs=0, debug=8 | 64)),
-                 ("N32+shift0", dict(out_gs=0, debug=8 | 16 | 64))):
+                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("nofence(512)", dict(out_gs=0, debug=8 | 512)),
+                 ("defer-commit(1024)", dict(out_gs=0, debug=8 | 1024)), ("nofence+defer", dict(out_gs=0, debug=8 | 512 | 1024)),
+                 ("1tap", dict(out_gs=0, debug=8 | 256)), ("1tap+nofence", dict(out_gs=0, debug=8 | 256 | 512)),
+                 ("1tap+defer", dict(out_gs=0, debug=8 | 256 | 1024)), ("full nofence+defer", dict(out_gs=32, residual=x, debug=512 | 1024))):
     buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device=dev)
     for rep in range(2):
         buf.zero_()
@@ -41,5 +46,8 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid"
     p1 = (b[2, 1:6, 2] - b[2, 1:6, 1]).mean(); p2 = (b[2, 1:6, 3] - b[2, 1:6, 2]).mean()
     mma = (b[1, 1:6, 14] - b[1, 1:6, 13]).mean(); tile = (b[2, 2:6, 3] - b[2, 1:5, 3]).mean()
     seg = lambda a, c: float((b[2, 1:6, a] - b[2, 1:6, c]).mean())
+    slab = [float((b[1, 1:6, k * 3 + 2] - b[1, 1:6, k * 3 + 1]).mean()) for k in range(4)]
+    swait = [float((b[1, 1:6, k * 3 + 1] - b[1, 1:6, k * 3 + 0]).mean()) for k in range(4)]
+    print(f"{name:18s} slab issue {[round(v) for v in slab]} slab wait {[round(v) for v in swait]} tempty wait {float((b[1,1:6,13]-b[1,1:6,12]).mean()):.0f}")
     print(f"{name:18s} pass1={p1:7.0f} pass2={p2:7.0f} mma_tile={mma:7.0f} tile_period={tile:7.0f} | top->wait {seg(0, 7):6.0f} wait {seg(1, 0):6.0f} "
           f"loop {seg(4, 2):6.0f} shfl {seg(5, 4):6.0f} bar9 {seg(6, 5):6.0f} flush {seg(3, 6):6.0f}")
