@@ -544,6 +544,48 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
   const int pa0 = blockIdx.x * p.pos_per_block;     // first allocation position of this block
   const int q_first = pa0 - p.G;
   const int n0 = q_first > 0 ? (int)p.dPH.div(p.dPW.div((uint32_t)min(q_first, p.Q - 1))) : 0;
+  // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row).
+  // Items are processed in batches of kPrepBatch with all loads issued first (memory-level parallelism).
+  // thread = (chunk j, position lane); it walks positions pl, pl + pstep, ...  (x, y, n) are advanced incrementally, so the
+  // per-item cost of locating the source pixel is a few adds instead of two divisions
+  const int pstep = kPrepThreads / nch;             // nch in {2, 4, 8, 16}
+  const int j = threadIdx.x % nch;
+  int pl = threadIdx.x / nch;
+  int x, y, n;                                      // coordinates of position pa0 + pl (may be in the guard: q < 0)
+  {
+    const int q = pa0 + pl - p.G;
+    const int qq = q < 0 ? 0 : q;
+    const uint32_t R = p.dPW.div((uint32_t)qq);
+    x = qq - (int)R * p.PW; n = (int)p.dPH.div(R); y = (int)R - n * p.PH;
+    if (q < 0) x += q;                              // negative x marks guard positions until it wraps to >= 0
+  }
+  const bool has_data = j * 8 < S.C;
+  // The first batch of loads does not depend on the coefficients: issue it BEFORE the statistics -> coefficient phase
+  // (two barriers and a chain of dependent global loads), whose latency it then hides.
+  float4 v0[kPrepBatch], v1[kPrepBatch];
+  int meta[kPrepBatch];  // -2: nothing to write, -1: zero fill, else image slot | j << 8
+  size_t off[kPrepBatch];
+  auto load_batch = [&]() {
+#pragma unroll
+    for (int u = 0; u < kPrepBatch; ++u) {
+      const int pa = pa0 + pl + u * pstep;
+      meta[u] = -2;
+      if (pl + u * pstep < p.pos_per_block && pa < p.Qalloc) {
+        meta[u] = -1;
+        off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
+        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
+          const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
+          const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
+          v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
+          meta[u] = (n - n0) | (j << 8);
+        }
+      }
+      // advance to the next owned position
+      x += pstep;
+      while (x >= p.PW) { x -= p.PW; if (++y == p.PH) { y = 0; ++n; } }
+    }
+  };
+  load_batch();
   if (p.mode != 0) {
     const int G = S.C / S.gs;
     if (threadIdx.x < 2 * G) {  // fp64 only for the statistics
@@ -596,44 +638,7 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
     }
     __syncthreads();
   }
-  // lane layout: consecutive lanes = the 8-channel chunks of one pixel (coalesced 32-byte reads of one NHWC row).
-  // Items are processed in batches of kPrepBatch with all loads issued first (memory-level parallelism).
-  // thread = (chunk j, position lane); it walks positions pl, pl + pstep, ...  (x, y, n) are advanced incrementally, so the
-  // per-item cost of locating the source pixel is a few adds instead of two divisions
-  const int pstep = kPrepThreads / nch;             // nch in {2, 4, 8, 16}
-  const int j = threadIdx.x % nch;
-  int pl = threadIdx.x / nch;
-  int x, y, n;                                      // coordinates of position pa0 + pl (may be in the guard: q < 0)
-  {
-    const int q = pa0 + pl - p.G;
-    const int qq = q < 0 ? 0 : q;
-    const uint32_t R = p.dPW.div((uint32_t)qq);
-    x = qq - (int)R * p.PW; n = (int)p.dPH.div(R); y = (int)R - n * p.PH;
-    if (q < 0) x += q;                              // negative x marks guard positions until it wraps to >= 0
-  }
-  const bool has_data = j * 8 < S.C;
-  for (; pl < p.pos_per_block; pl += kPrepBatch * pstep) {
-    float4 v0[kPrepBatch], v1[kPrepBatch];
-    int meta[kPrepBatch];  // -2: nothing to write, -1: zero fill, else image slot | j << 8
-    size_t off[kPrepBatch];
-#pragma unroll
-    for (int u = 0; u < kPrepBatch; ++u) {
-      const int pa = pa0 + pl + u * pstep;
-      meta[u] = -2;
-      if (pl + u * pstep < p.pos_per_block && pa < p.Qalloc) {
-        meta[u] = -1;
-        off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
-        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
-          const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
-          const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
-          v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
-          meta[u] = (n - n0) | (j << 8);
-        }
-      }
-      // advance to the next owned position
-      x += pstep;
-      while (x >= p.PW) { x -= p.PW; if (++y == p.PH) { y = 0; ++n; } }
-    }
+  for (;;) {
 #pragma unroll
     for (int u = 0; u < kPrepBatch; ++u) {
       if (meta[u] == -2) continue;
@@ -664,6 +669,9 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
       if (S.dst_raw != nullptr) *reinterpret_cast<uint4*>(S.dst_raw + off[u]) = raw;
       if (S.dst_raw_lo != nullptr) *reinterpret_cast<uint4*>(S.dst_raw_lo + off[u]) = raw_lo;
     }
+    pl += kPrepBatch * pstep;
+    if (pl >= p.pos_per_block) break;
+    load_batch();
   }
 }
 
