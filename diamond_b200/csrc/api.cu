@@ -362,8 +362,6 @@ struct SamplerGraph {
 
 struct dmd_denoiser {
   dmd_denoiser_config cfg;
-  cudaStream_t side = nullptr;                       // conditioning path runs here, forked / joined with events
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_tensors = 0;
   // state_dict indices
   int i_fourier = 0, i_actemb = 0, i_cp0w = 0, i_cp0b = 0, i_cp2w = 0, i_cp2b = 0, i_normout_w = 0, i_normout_b = 0;
@@ -623,23 +621,11 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
                 const int64_t* act, cudaStream_t st, int prescaled = 0) {
   const dmd_denoiser_config& c = h->cfg;
   const int HW = pl.H * pl.W;
-  // The conditioning path (embedding -> MLP -> all FiLM vectors) only needs the per-sample scalars of the pack kernel; it
-  // runs on a side stream next to prep + conv_in and joins before the first AdaGroupNorm consumer.  The event edges are
-  // captured like any other dependency when the sampler records its graph.
-  if (!h->side) {
-    DMD_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    DMD_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    DMD_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t main_st = st;
   DMD_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st));
   pack_denoiser_input_kernel<<<dim3((HW + 255) / 256, pl.B), 256, 0, st>>>(
       noisy, obs, sigma, sigma_is_scalar, pl.xin, pl.cs, c.num_steps_conditioning * c.img_channels, c.img_channels,
       pl.CP_in, HW, c.sigma_data, c.sigma_offset_noise, prescaled);
   DMD_LAUNCH_OK();
-  DMD_CUDA(cudaEventRecord(h->ev_fork, main_st));
-  st = h->side;
-  DMD_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0));
   {
     const int total = pl.B * c.cond_channels;
     cond_embed_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.cs, act, h->ptrs[h->i_fourier], h->ptrs[h->i_actemb], pl.cemb,
@@ -650,19 +636,11 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
   if (linear_launch(pl.chid, h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, pl.B, c.cond_channels, c.cond_channels, 0, st)) return 1;
   if (linear_launch(pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film,
                     pl.B, c.cond_channels, h->film_rows, 0, st)) return 1;
-  DMD_CUDA(cudaEventRecord(h->ev_join, st));
-  st = main_st;
-  bool joined = false;
   for (const Op& op : pl.ops) {
-    if (!joined && !(op.kind == OP_CONV || (op.kind == OP_PREP && op.prep.mode != 1))) {
-      DMD_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));   // first consumer of a FiLM vector (or attention: be conservative)
-      joined = true;
-    }
     if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
     else if (op.kind == OP_PREP) { if (prep_launch(op.prep, op.prep_nsrc, st)) return 1; }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
-  if (!joined) DMD_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   return 0;
 }
 
@@ -705,9 +683,6 @@ extern "C" void dmd_denoiser_destroy(dmd_denoiser* h) {
   if (!h) return;
   if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
   if (h->graph.cap_stream) cudaStreamDestroy(h->graph.cap_stream);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_tensors; }
