@@ -249,9 +249,9 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
             "prep_us_per_launch": ms_prep * 1e3,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            # dram__bytes_read+write of conv_tc_kernel from profiles/r01_prof_conv_v4_summary.csv (B=32; that capture also
+            # dram__bytes_read+write of conv_tc_kernel from profiles/r01_prof_conv_v5_summary.csv (B=32; that capture also
             # reads the 33.5 MB residual; the operand and the output mostly stay in the 126 MB L2)
-            "traffic": 53.8e6, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
+            "traffic": 54.1e6, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
             "us_per_launch": ms * 1e3, "flop_per_launch": flops, "peak_source": peaks_src + " bf16 burst (fp16 and bf16 share the tensor-pipe rate)"}
 
 
