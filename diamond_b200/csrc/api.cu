@@ -1,4 +1,7 @@
 // libdiamond_b200.so — C ABI (include/diamond_b200.h) over the sm_100a kernels.
+#include <cstdlib>
+#include <mutex>
+#include <map>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -64,6 +67,19 @@ static size_t plc16_bytes(int B, int H, int W, int C) {
 }
 extern "C" size_t dmd_plc16_bytes(int B, int H, int W, int C) { return plc16_bytes(B, H, W, C); }
 
+// Tuning knobs (read once per name): integers from the environment, for sweeps on the GPU box without a rebuild.
+static int tune_int(const char* name, int dflt) {
+  static std::mutex mu;
+  static std::map<std::string, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(name);
+  if (it != cache.end()) return it->second;
+  const char* v = getenv(name);
+  const int r = (v && *v) ? atoi(v) : dflt;
+  cache[name] = r;
+  return r;
+}
+
 static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* tmem_cols) {
   DMD_CHECK(d->src0 && d->out && d->wpk, "conv: null src0/out/wpk");
   DMD_CHECK(d->taps == 9 || d->taps == 1, "conv: taps must be 1 or 9 (got %d)", d->taps);
@@ -127,6 +143,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   int stages = (int)(budget / (long long)L0.slab_bytes);
   if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
+  { const int cap = tune_int("DMD_CONV_MAX_STAGES", kMaxStages); if (cap >= 2 && stages > cap) stages = cap; }
   DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
   p->stages = stages;
   *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages).total;
@@ -210,7 +227,7 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   DMD_CHECK(g.PH * g.PW >= 32, "prep: image too small");
   // a block touches at most 2 images; low-resolution levels get smaller blocks so that the grid still covers the SMs
   int ppb = g.PH * g.PW >= 256 ? 256 : (g.PH * g.PW / 32) * 32;
-  while (ppb > 64 && (g.Qalloc + ppb - 1) / ppb < 2 * 148) ppb >>= 1;
+  while (ppb > 64 && (g.Qalloc + ppb - 1) / ppb < tune_int("DMD_PREP_MIN_BLOCKS", 2 * 148)) ppb >>= 1;
   ppb = (ppb / 32) * 32;
   p->pos_per_block = ppb;
   DMD_CHECK(d->C0 / (d->gs0 > 0 ? d->gs0 : 8) <= 4 || d->mode == 0, "prep: at most 4 groups per source");
@@ -281,9 +298,10 @@ static int linear_launch(const float* in, const float* W, const float* bias, flo
   if (init_kernels()) return 1;
   // enough blocks to cover the SMs: 8, 16 or 32 output features per block
   const int by = (B + 31) / 32;
-  if ((long long)((F + 31) / 32) * by >= 296)
+  const int forceJ = tune_int("DMD_LINEAR_J", 0);
+  if (forceJ == 4 || (forceJ == 0 && (long long)((F + 31) / 32) * by >= 296))
     linear_kernel<4><<<dim3((F + 31) / 32, by), 256, (size_t)(32 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
-  else if ((long long)((F + 15) / 16) * by >= 148)
+  else if (forceJ == 2 || (forceJ == 0 && (long long)((F + 15) / 16) * by >= 148))
     linear_kernel<2><<<dim3((F + 15) / 16, by), 256, (size_t)(16 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
   else
     linear_kernel<1><<<dim3((F + 7) / 8, by), 256, (size_t)(8 + 32) * kLinChunk * sizeof(float), st>>>(in, W, bias, out, B, K, F, silu, accumulate, hw_perm);
