@@ -33,10 +33,7 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("stats+
 
 print("==== summary (cycles, mean over tiles 1..5 of CTA 0)")
 for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid", dict(out_gs=0, residual=x)), ("stats+resid", dict(out_gs=32, residual=x)),
-                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("nofence(512)", dict(out_gs=0, debug=8 | 512)),
-                 ("defer-commit(1024)", dict(out_gs=0, debug=8 | 1024)), ("nofence+defer", dict(out_gs=0, debug=8 | 512 | 1024)),
-                 ("1tap", dict(out_gs=0, debug=8 | 256)), ("1tap+nofence", dict(out_gs=0, debug=8 | 256 | 512)),
-                 ("1tap+defer", dict(out_gs=0, debug=8 | 256 | 1024)), ("full nofence+defer", dict(out_gs=32, residual=x, debug=512 | 1024))):
+                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("noMMA(dbg2)", dict(out_gs=0, debug=8 | 2))):
     buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device=dev)
     for rep in range(2):
         buf.zero_()
