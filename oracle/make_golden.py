@@ -124,6 +124,131 @@ def make_actor_critic():
     print("actor_critic_default logits rms", float(torch.stack(logits).pow(2).mean().sqrt()))
 
 
+TRAIN_CASES = {
+    # default agent config, one autoregressive step, every sample valid
+    "denoiser_default_training": dict(case="denoiser_default", b=2, seq=1, mask_off=[], rng_seed=21, dseed=301),
+    # small net, two autoregressive steps (the second conditions on the first step's denoised frame), one padded sample
+    "denoiser_small_training": dict(case="denoiser_small_heun", b=3, seq=2, mask_off=[(1, -1)], rng_seed=22, dseed=302),
+}
+
+
+def make_denoiser_training():
+    """Reference Denoiser.forward (training loss, denoiser.py:93-122) + backward on seeded weights / batches.  The fixture
+    records the standard-normal draws the reference consumed from the global RNG, the loss and a gradient summary."""
+    ns = ref_import.load()
+    D = ns.diffusion
+    for name, tc in TRAIN_CASES.items():
+        c = CASES[tc["case"]]
+        inner = c["inner"]
+        sd = O.seeded_state_dict(O.inner_model_shapes(inner), c["wseed"])
+        den = build_reference(ns, inner, sd).train()
+        sig_cfg = O.SigmaDistCfg()
+        den.setup_training(D.SigmaDistributionConfig(sig_cfg.loc, sig_cfg.scale, sig_cfg.sigma_min, sig_cfg.sigma_max))
+        rng = np.random.default_rng(tc["dseed"])
+        b, n, T = tc["b"], inner.num_steps_conditioning, inner.num_steps_conditioning + tc["seq"]
+        ch, h, w = inner.img_channels, c["h"], c["w"]
+        obs = torch.from_numpy(rng.integers(0, 256, size=(b, T, ch, h, w)).astype(np.float32)).div(255).mul(2).sub(1)
+        act = torch.from_numpy(rng.integers(0, inner.num_actions, size=(b, T)).astype(np.int64))
+        mask = torch.ones(b, T, dtype=torch.bool)
+        for (bi, ti) in tc["mask_off"]:
+            mask[bi, ti] = False
+        batch = ns.data.Batch(obs=obs, act=act, rew=torch.zeros(b, T), end=torch.zeros(b, T, dtype=torch.long),
+                              trunc=torch.zeros(b, T, dtype=torch.long), mask_padding=mask, info=[{}] * b, segment_ids=[None] * b)
+        torch.manual_seed(tc["rng_seed"])
+        loss, logs = den(batch)
+        loss.backward()
+        # replay the RNG stream: per step randn(b) [sigma], randn(b, c, 1, 1) [offset], randn(b, c, h, w) [noise]
+        torch.manual_seed(tc["rng_seed"])
+        raw_sigma, raw_off, raw_noise = [], [], []
+        for _ in range(tc["seq"]):
+            raw_sigma.append(torch.randn(b)); raw_off.append(torch.randn(b, ch, 1, 1)); raw_noise.append(torch.randn(b, ch, h, w))
+        grads = [(k, p.grad) for k, p in den.inner_model.named_parameters()]
+        assert all(g is not None for _, g in grads)
+        keys, norms, samples = O.grad_summary(grads)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, weights_checksum=np.float64(O.state_checksum(sd)), obs=obs.numpy(), act=act.numpy(),
+                            mask_padding=mask.numpy(), raw_sigma=torch.stack(raw_sigma).numpy(), raw_offset=torch.stack(raw_off).numpy(),
+                            raw_noise=torch.stack(raw_noise).numpy(), loss=np.float64(loss.item()), grad_keys=np.array(keys),
+                            grad_norms=norms, grad_samples=samples)
+        print(name, "loss", loss.item(), "grad norm", float(np.sqrt((norms**2).sum())), "size", os.path.getsize(path))
+
+
+class _ScriptedEnv:
+    """Deterministic stand-in for TorchEnv / WorldModelEnv (envs/env.py, world_model_env.py:58-106 surface used by
+    env_loop.py): returns pre-generated observations, rewards and termination flags, ignores the action."""
+
+    def __init__(self, obs_seq, rew, end, trunc, final_obs, num_actions):
+        self.obs_seq, self.rew, self.end, self.trunc, self.final_obs = obs_seq, rew, end, trunc, final_obs
+        self.num_envs, self.num_actions, self.t = obs_seq.size(1), num_actions, 0
+
+    def reset(self, seed=None):
+        self.t = 0
+        return self.obs_seq[0], {}
+
+    def step(self, act):
+        t = self.t
+        dead = torch.logical_or(self.end[t].bool(), self.trunc[t].bool())
+        info = {"final_observation": self.final_obs[t]} if dead.any() else {}
+        self.t += 1
+        return self.obs_seq[t + 1], self.rew[t], self.end[t], self.trunc[t], info
+
+
+def make_actor_critic_training():
+    """Reference ActorCritic.forward (loss, actor_critic.py:75-98) through the reference's own make_env_loop
+    (env_loop.py:12-74) over a scripted environment with two terminations, + backward (BPTT through the LSTM)."""
+    ns = ref_import.load()
+    AC = ns.actor_critic
+    cfg = O.ActorCriticCfg()
+    sd = O.seeded_actor_critic_state_dict(cfg, 556)
+    ac = AC.ActorCritic(AC.ActorCriticConfig(cfg.lstm_dim, cfg.img_channels, cfg.img_size, list(cfg.channels), list(cfg.down), cfg.num_actions))
+    ac.load_state_dict(sd)
+    lc = O.ActorCriticLossCfg(backup_every=5)
+    rng = np.random.default_rng(92)
+    T, b = lc.backup_every, 4
+    obs_seq = torch.from_numpy(rng.integers(0, 256, size=(T + 1, b, 3, 64, 64)).astype(np.float32)).div(255).mul(2).sub(1)
+    rew = torch.from_numpy(rng.choice([-1.0, 0.0, 0.0, 2.0], size=(T, b)).astype(np.float32))
+    end = torch.zeros(T, b, dtype=torch.long); trunc = torch.zeros(T, b, dtype=torch.long)
+    end[1, 2] = 1; trunc[3, 0] = 1; end[T - 1, 1] = 1   # mid-rollout termination, truncation, termination on the last step
+    final_obs = {}
+    for t in range(T):
+        dead = torch.logical_or(end[t].bool(), trunc[t].bool())
+        if dead.any():
+            final_obs[t] = torch.from_numpy(rng.integers(0, 256, size=(int(dead.sum()), 3, 64, 64)).astype(np.float32)).div(255).mul(2).sub(1)
+    env = _ScriptedEnv(obs_seq, rew, end, trunc, final_obs, cfg.num_actions)
+    ac.setup_training(env, AC.ActorCriticLossConfig(lc.backup_every, lc.gamma, lc.lambda_, lc.weight_value_loss, lc.weight_entropy_loss))
+    torch.manual_seed(31)
+    # capture what the env loop hands to the loss (the sampled actions are data for the oracle)
+    captured = {}
+    real_loop = ac.env_loop
+
+    class _Tap:
+        def send(self, n):
+            out = real_loop.send(n)
+            captured["out"] = out
+            return out
+    ac.env_loop = _Tap()
+    loss, metrics = ac()
+    loss.backward()
+    _, act, rew_o, end_o, trunc_o, logits, val, val_bootstrap, _ = captured["out"]
+    grads = [(k, p.grad) for k, p in ac.named_parameters()]
+    assert all(g is not None for _, g in grads)
+    keys, norms, samples = O.grad_summary(grads)
+    path = os.path.join(OUT, "actor_critic_training.npz")
+    fo_t = np.array(sorted(final_obs.keys()), np.int64)
+    np.savez_compressed(path, weights_checksum=np.float64(O.state_checksum(sd)), obs_seq=obs_seq.numpy(), rew=rew.numpy(), end=end.numpy(),
+                        trunc=trunc.numpy(), final_obs_t=fo_t, **{f"final_obs_{t}": final_obs[t].numpy() for t in final_obs},
+                        act=act.numpy(), logits=logits.detach().numpy(), val=val.detach().numpy(), val_bootstrap=val_bootstrap.numpy(),
+                        loss=np.float64(loss.item()), metric_keys=np.array(list(metrics.keys())),
+                        metric_vals=np.array([float(v) for v in metrics.values()], np.float64),
+                        grad_keys=np.array(keys), grad_norms=norms, grad_samples=samples)
+    print("actor_critic_training loss", loss.item(), "grad norm", float(np.sqrt((norms**2).sum())), "size", os.path.getsize(path))
+
+
 if __name__ == "__main__":
-    main()
-    make_actor_critic()
+    which = sys.argv[1:] or ["inference", "training"]
+    if "inference" in which:
+        main()
+        make_actor_critic()
+    if "training" in which:
+        make_denoiser_training()
+        make_actor_critic_training()
