@@ -162,6 +162,31 @@ def test_conv_with_fused_skip_projection():
     assert _rel(got, ref) < 2e-5, _rel(got, ref)
 
 
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 64), (64, 128)])
+def test_conv_dgrad_is_the_forward_kernel_with_transposed_flipped_weights(cin, cout):
+    """Building block of the training rows: backward-data of a 3x3 / stride-1 / pad-1 convolution
+    (every ResBlock conv, blocks.py:137-139) is the SAME implicit GEMM on the output gradient with the weights transposed
+    (Cin <-> Cout) and the taps flipped, so it runs on the tcgen05 kernel unchanged.  Checked against torch autograd."""
+    dev = _dev()
+    from diamond_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    b, h, w = 2, 32, 32
+    x = torch.randn(b, cin, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    gy = torch.randn(b, cout, h, w, generator=g)
+    (gx,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), x, gy)
+    wt_t = wt.transpose(0, 1).flip(2, 3).contiguous()            # [cin, cout, 3, 3]
+    gx16 = F.conv2d(_h(gy).double(), _h(wt_t).double(), padding=1).float()
+    assert _rel(gx16, gx) < 2e-3                                   # the identity itself (fp16 operands vs exact)
+    wpk, cpad = ops.pack_conv_weight(wt_t.to(dev), cout)
+    out, _ = ops.conv2d_fprop(ops.nchw_to_nhwc(gy.to(dev)), wpk, cin, cpad, cout, 9)
+    got = ops.nhwc_to_nchw(out).cpu()
+    assert got.shape == gx.shape
+    assert _rel(got, gx16) < 2e-5, _rel(got, gx16)
+    assert _rel(got, gx) < 2e-3, _rel(got, gx)
+
+
 def test_conv_linearity_and_zero():
     """size-independent properties: conv(0)=bias, conv(a+b)-bias = (conv(a)-bias)+(conv(b)-bias) up to fp16 rounding."""
     dev = _dev()
