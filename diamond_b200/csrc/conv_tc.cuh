@@ -11,16 +11,19 @@
 // between neighbouring rows / images, so tap (dy,dx) of a 3x3 window is simply position q + dy*PW + dx.  The tensor is
 // stored as one plane per 8-channel chunk:   plane[j][G + q] = 8 fp16 channels = 16 bytes   (G = PW+1 zero guard
 // positions in front, PW+1 behind the last tile).  A 128-row tile needs, per 16 input channels ("slab"), positions
-// [q0-PW-1, q0+128+PW+1) of two planes: two CONTIGUOUS byte ranges.  One thread fetches them with cp.async.bulk straight
+// [q0-PW-1, q0+128+PW+1) of two planes: two CONTIGUOUS byte ranges.  They are fetched with cp.async.bulk straight
 // into the UMMA no-swizzle K-major shared-memory layout  [2 chunks][P positions][16 B]  (LBO = Palloc*16, SBO = 128),
 // and every tap reads the same slab through a descriptor whose start address is shifted by (dy*PW+dx)*16 B.
 //
 // Roles (320 threads, one CTA per SM, contiguous balanced tile ranges):
 //   warp 0      producer: mbarrier expect_tx + 2 bulk copies per slab into a deep ring (empty/full mbarriers)
-//   warp 1      MMA     : one thread issues tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap) from precomputed
-//                         descriptor words; tcgen05.commit frees the slab / publishes the TMEM accumulator
+//   warp 1      MMA     : tcgen05.mma (M=128, N=CoutPad, K=16) per (slab, tap) from precomputed descriptor words;
+//                         tcgen05.commit frees the slab / publishes the TMEM accumulator.  A fused 1x1 skip projection
+//                         is extra centre-tap slabs on the same accumulator.
+//               Both warps walk their loops CONVERGED and an elect.sync lane issues (uniform-register operands).
 //   warps 2-9   epilogue: TMEM -> registers (+bias) -> shared staging (transpose) -> coalesced 16-byte global stores with
-//                         the residual added on the way; per-tile deterministic GroupNorm partial sums -> fp64 atomics
+//                         the (prefetched) residual added on the way; GroupNorm partial sums run in registers across the
+//                         single-image tiles of the CTA and are reduced once per image -> fp64 atomics
 // Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
 // TMEM holds two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
