@@ -19,3 +19,60 @@ def init_lstm(model: nn.Module) -> None:
             p.data[(n // 4):(n // 2)].fill_(1)  # forget-gate bias
         elif "bias_hh" in name:
             p.data.fill_(0)
+
+
+# ----------------------------------------------------------------------------------------------- data-parallel plumbing
+# SURVEY.md 8 a26.  The reference wraps each agent module in torch DDP (utils.py:105-106, trainer.py:110) and relies on
+# autograd hooks to average gradients.  A native executor produces all gradients of a module in one C-ABI call, outside
+# autograd, so the averaging is explicit: flat fp32 buckets, one all_reduce per bucket (NCCL over NVLink on GPUs, gloo in
+# the CPU tests), same result as DDP (sum over ranks / world size).
+
+
+def broadcast_if_needed(*args):
+    """utils.py:97-102: every rank ends up with rank 0's objects; a no-op without a process group."""
+    import torch.distributed as dist
+
+    objects = list(args)
+    if dist.is_available() and dist.is_initialized():
+        dist.broadcast_object_list(objects, src=0)
+    return objects
+
+
+def allreduce_gradients(params, bucket_bytes: int = 32 << 20, group=None) -> int:
+    """Average `.grad` of `params` over the process group in flat buckets of <= bucket_bytes (one collective each; with
+    NVSwitch the cost is launch latency, not link count, so buckets are large).  Parameters without a gradient are treated
+    as zero on this rank (DDP's find_unused_parameters semantics) so that every rank issues identical collectives.
+    Returns the number of all_reduce calls issued (0 without a process group)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    params = [p for p in params if p.requires_grad]
+    calls, i = 0, 0
+    while i < len(params):
+        j, nbytes = i, 0
+        while j < len(params) and (j == i or nbytes + params[j].numel() * 4 <= bucket_bytes):
+            nbytes += params[j].numel() * 4
+            j += 1
+        chunk = params[i:j]
+        flat = torch.zeros(sum(p.numel() for p in chunk), dtype=torch.float32, device=chunk[0].device)
+        off = 0
+        for p in chunk:
+            if p.grad is not None:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for p in chunk:
+            g = flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += p.numel()
+        calls += 1
+        i = j
+    return calls

@@ -36,3 +36,58 @@ def test_two_rank_reduction_and_sharding():
     assert sum0 != sum1                      # ranks imagine different envs
     assert ms0 == ms1 == [11.0, 20.0]        # MAX over ranks, identical everywhere
     assert abs(agg0 - 2 * 8 / 11e-3) < 1e-6  # whole-job frames/s = all ranks' frames / max time
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from diamond_b200.utils import allreduce_gradients, broadcast_if_needed
+
+    def make():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.SiLU(), torch.nn.Flatten(), torch.nn.Linear(8 * 36, 5))
+
+    g = torch.Generator().manual_seed(100 + rank)            # every rank trains on its own shard
+    x, y = torch.randn(4, 3, 6, 6, generator=g), torch.randn(4, 5, generator=g)
+    ref = DDP(make())                                       # what the reference does (utils.py:105-106)
+    torch.nn.functional.mse_loss(ref(x), y).backward()
+    mine = make()
+    torch.nn.functional.mse_loss(mine(x), y).backward()
+    local = [p.grad.clone() for p in mine.parameters()]
+    calls = allreduce_gradients(list(mine.parameters()), bucket_bytes=1024)   # small buckets: several collectives
+    same = all(torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-7) for a, b in zip(mine.parameters(), ref.module.parameters()))
+    changed = any(not torch.equal(a, p.grad) for a, p in zip(local, mine.parameters()))
+    (seed,) = broadcast_if_needed(1234 + rank)
+    q.put((rank, same, changed, calls, seed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_torch_ddp():
+    """explicit bucketed gradient averaging == the DDP wrapper the reference uses."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, changed, calls, seed in out:
+        assert same and changed
+        assert calls >= 2                                    # 1 KB buckets: conv / linear weights go separately
+        assert seed == 1234                                  # rank 0's object everywhere (utils.py:97-102)
+
+
+def test_allreduce_gradients_is_a_noop_without_a_process_group():
+    from diamond_b200.utils import allreduce_gradients
+
+    lin = torch.nn.Linear(3, 2)
+    lin(torch.ones(1, 3)).sum().backward()
+    before = lin.weight.grad.clone()
+    assert allreduce_gradients(list(lin.parameters())) == 0
+    assert torch.equal(before, lin.weight.grad)
