@@ -244,11 +244,40 @@ def make_actor_critic_training():
     print("actor_critic_training loss", loss.item(), "grad norm", float(np.sqrt((norms**2).sum())), "size", os.path.getsize(path))
 
 
+def make_rew_end():
+    """Reference RewEndModel.predict_rew_end: a 3-step burn-in call that returns the LSTM state, then two
+    single-step calls carrying it -- the way WorldModelEnv uses it (world_model_env.py:96-105, :120-129)."""
+    ns = ref_import.load()
+    R = ns.rew_end_model
+    cfg = O.RewEndCfg()
+    sd = O.seeded_state_dict(O.rew_end_shapes(cfg), 777)
+    m = R.RewEndModel(R.RewEndModelConfig(cfg.lstm_dim, cfg.img_channels, cfg.img_size, cfg.cond_channels, list(cfg.depths),
+                                          list(cfg.channels), list(cfg.attn_depths), cfg.num_actions)).eval()
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == O.rew_end_shapes(cfg)
+    m.load_state_dict(sd)
+    rng = np.random.default_rng(93)
+    b = 3
+    frames = torch.from_numpy(rng.integers(0, 256, size=(b, 6, 3, 64, 64)).astype(np.float32)).div(255).mul(2).sub(1)
+    act = torch.from_numpy(rng.integers(0, cfg.num_actions, size=(b, 5)).astype(np.int64))
+    out = {}
+    with torch.no_grad():
+        lr, le, hc = m.predict_rew_end(frames[:, 0:3], act[:, 0:3], frames[:, 1:4])
+        out.update(burn_rew=lr.numpy(), burn_end=le.numpy())
+        for k in (3, 4):
+            lr, le, hc = m.predict_rew_end(frames[:, k:k + 1], act[:, k:k + 1], frames[:, k + 1:k + 2], hc)
+            out.update({f"step{k}_rew": lr.numpy(), f"step{k}_end": le.numpy()})
+    path = os.path.join(OUT, "rew_end_default.npz")
+    np.savez_compressed(path, weights_checksum=np.float64(O.state_checksum(sd)), frames=frames.numpy(), act=act.numpy(),
+                        hx=hc[0].numpy(), cx=hc[1].numpy(), **out)
+    print("rew_end_default logits rms", float(np.sqrt((out["burn_rew"] ** 2).mean())), "size", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["inference", "training"]
     if "inference" in which:
         main()
         make_actor_critic()
+        make_rew_end()
     if "training" in which:
         make_denoiser_training()
         make_actor_critic_training()

@@ -57,3 +57,23 @@ def test_oracle_sampler_matches_reference_golden(golden_dir, name):
     diff = (got - ref).abs()
     assert float((diff > 1e-4).float().mean()) < 2e-3, float(diff.max())
     assert torch.allclose(x, torch.from_numpy(g["sample_x"]), atol=0.5)
+
+
+def test_rew_end_oracle_matches_reference_golden(golden_dir):
+    """SURVEY.md 8 f1 (next row): RewEndModel.predict_rew_end restated and pinned ahead of its native executor."""
+    torch.set_num_threads(8)
+    g = _load(golden_dir, "rew_end_default")
+    cfg = O.RewEndCfg()
+    sd = O.seeded_state_dict(O.rew_end_shapes(cfg), 777)
+    assert abs(O.state_checksum(sd) - float(g["weights_checksum"])) < 1e-6 * float(g["weights_checksum"])
+    frames, act = torch.from_numpy(g["frames"]), torch.from_numpy(g["act"])
+    with torch.no_grad():
+        lr, le, hc = O.predict_rew_end(frames[:, 0:3], act[:, 0:3], frames[:, 1:4], sd, cfg)
+        assert torch.allclose(lr, torch.from_numpy(g["burn_rew"]), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(le, torch.from_numpy(g["burn_end"]), rtol=1e-4, atol=1e-5)
+        for k in (3, 4):
+            lr, le, hc = O.predict_rew_end(frames[:, k:k + 1], act[:, k:k + 1], frames[:, k + 1:k + 2], sd, cfg, hc)
+            assert torch.allclose(lr, torch.from_numpy(g[f"step{k}_rew"]), rtol=1e-4, atol=1e-5)
+            assert torch.allclose(le, torch.from_numpy(g[f"step{k}_end"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(hc[0], torch.from_numpy(g["hx"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(hc[1], torch.from_numpy(g["cx"]), rtol=1e-4, atol=1e-5)
