@@ -52,6 +52,11 @@ class SamplerConfigC(C.Structure):
     ]
 
 
+class ConvPlanInfo(C.Structure):  # dmd_conv_plan_info
+    _fields_ = [("tiles", _i), ("kslabs", _i), ("stages", _i), ("tmem_cols", _i),
+                ("smem_bytes", C.c_ulonglong), ("weight_bytes", C.c_ulonglong)]
+
+
 # name -> (restype, argtypes); this table is also what tests use to check that every symbol is exported
 SIGNATURES = {
     "dmd_version": (_i, []),
@@ -60,6 +65,8 @@ SIGNATURES = {
     "dmd_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dmd_plc16_bytes": (_sz, [_i, _i, _i, _i]),
     "dmd_prep_act": (_i, [C.POINTER(PrepDesc), _vp]),
+    "dmd_prep_plan": (_i, [C.POINTER(PrepDesc), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dmd_conv_plan": (_i, [C.POINTER(ConvDesc), C.POINTER(ConvPlanInfo)]),
     "dmd_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp]),
     "dmd_gn_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dmd_attn_fwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _vp]),

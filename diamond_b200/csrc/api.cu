@@ -240,6 +240,21 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
 static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
   return launch_pdl(prep_act_kernel, dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), dim3(kPrepThreads), 0, st, p);
 }
+extern "C" int dmd_prep_plan(const dmd_prep_desc* d, int* blocks, int* pos_per_block, int* sources) {
+  DMD_CHECK(d && blocks && pos_per_block && sources, "prep_plan: null argument");
+  PrepParams p; int nsrc;
+  if (prep_fill(d, &p, &nsrc)) return 1;
+  *blocks = (p.Qalloc + p.pos_per_block - 1) / p.pos_per_block; *pos_per_block = p.pos_per_block; *sources = nsrc;
+  return 0;
+}
+extern "C" int dmd_conv_plan(const dmd_conv_desc* d, dmd_conv_plan_info* out) {
+  DMD_CHECK(d && out, "conv_plan: null argument");
+  ConvParams p; size_t smem; int cols;
+  if (conv_fill(d, &p, &smem, &cols)) return 1;
+  out->tiles = p.num_tiles; out->kslabs = (p.Cin + p.Cextra) / 16; out->stages = p.stages; out->tmem_cols = cols;
+  out->smem_bytes = smem; out->weight_bytes = conv_weight_bytes(p.taps, p.Cin, p.Cextra, p.CoutPad);
+  return 0;
+}
 extern "C" int dmd_prep_act(const dmd_prep_desc* d, void* stream) {
   PrepParams p; int nsrc;
   if (prep_fill(d, &p, &nsrc)) return 1;

@@ -105,6 +105,20 @@ typedef struct dmd_conv_desc {
 
 int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);
 
+/* Host-only twins of dmd_conv2d_fprop / dmd_prep_act: run exactly the same validation and planning, touch neither the
+ * device nor the pointed-to memory (pointers are only tested for NULL), and report the launch plan.  They make the
+ * shape limits and the error behaviour (return code + dmd_last_error()) testable without a GPU. */
+typedef struct dmd_conv_plan_info {
+  int tiles;             /* 128-row tiles (one CTA per SM walks a contiguous range of them) */
+  int kslabs;            /* 16-channel K slabs per tile, fused projection included */
+  int stages;            /* depth of the shared-memory slab ring */
+  int tmem_cols;         /* TMEM columns per accumulator (two are allocated) */
+  unsigned long long smem_bytes;    /* dynamic shared memory of the launch */
+  unsigned long long weight_bytes;  /* resident packed weights */
+} dmd_conv_plan_info;
+int dmd_conv_plan(const dmd_conv_desc* d, dmd_conv_plan_info* out);
+int dmd_prep_plan(const dmd_prep_desc* d, int* blocks, int* pos_per_block, int* sources);
+
 /* GroupNorm partial sums of an NHWC tensor: stats[n][g] += (sum, sumsq) (blocks.py:28,43). */
 int dmd_gn_stats(const float* x, double* stats, int B, int HW, int C, int gs, void* stream);
 
