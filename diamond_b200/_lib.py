@@ -52,6 +52,12 @@ class SamplerConfigC(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):  # dmd_wgrad_desc
+    _fields_ = [("grad", _vp), ("act", _vp), ("Cg", _i), ("Ca", _i), ("B", _i), ("H", _i), ("W", _i), ("taps", _i),
+                ("dW", _vp), ("Cout", _i), ("Cin", _i), ("CinTot", _i), ("ci_off", _i), ("inv_scale", _vp),
+                ("accumulate", _i), ("partial", _vp), ("partial_bytes", _sz), ("debug", _i)]
+
+
 class ConvPlanInfo(C.Structure):  # dmd_conv_plan_info
     _fields_ = [("tiles", _i), ("kslabs", _i), ("stages", _i), ("tmem_cols", _i),
                 ("smem_bytes", C.c_ulonglong), ("weight_bytes", C.c_ulonglong)]
@@ -68,6 +74,9 @@ SIGNATURES = {
     "dmd_prep_plan": (_i, [C.POINTER(PrepDesc), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dmd_conv_plan": (_i, [C.POINTER(ConvDesc), C.POINTER(ConvPlanInfo)]),
     "dmd_conv2d_fprop": (_i, [C.POINTER(ConvDesc), _vp]),
+    "dmd_pack_conv_weight_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dmd_wgrad_partial_bytes": (_sz, []),
+    "dmd_conv2d_wgrad": (_i, [C.POINTER(WgradDesc), _vp]),
     "dmd_gn_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dmd_attn_fwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _vp]),
     "dmd_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -80,7 +89,11 @@ SIGNATURES = {
     "dmd_denoiser_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "dmd_denoiser_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmd_inner_model_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "dmd_sampler_sample": (_i, [_vp, C.POINTER(SamplerConfigC), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dmd_denoiser_train_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "dmd_denoiser_grad_layout": (C.c_longlong, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
+    "dmd_inner_model_forward_train": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmd_denoiser_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "dmd_sampler_sample": (_i, [_vp, C.POINTER(SamplerConfigC), _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "dmd_actor_critic_create": (_vp, [C.POINTER(ActorCriticConfigC)]),
     "dmd_actor_critic_destroy": (None, [_vp]),
     "dmd_actor_critic_num_tensors": (_i, [_vp]),
@@ -88,6 +101,10 @@ SIGNATURES = {
     "dmd_actor_critic_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp]),
     "dmd_actor_critic_workspace_bytes": (_sz, [_vp, _i]),
     "dmd_actor_critic_forward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmd_actor_critic_backward_scratch_bytes": (_sz, [_vp, _i]),
+    "dmd_actor_critic_grad_layout": (C.c_longlong, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
+    "dmd_actor_critic_backward": (_i, [_vp, _i] + [_vp] * 8 + [C.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmd_lambda_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_double, C.c_double, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

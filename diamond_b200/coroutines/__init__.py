@@ -1,13 +1,1 @@
-from functools import wraps
-
-
-def coroutine(func):
-    """Primes a generator so that the first `.send()` delivers a value (reference: src/coroutines/__init__.py)."""
-
-    @wraps(func)
-    def primed(*args, **kwargs):
-        gen = func(*args, **kwargs)
-        next(gen)
-        return gen
-
-    return primed
+from .env_loop import ImaginationLoop, make_env_loop

@@ -1,5 +1,6 @@
 // libdiamond_b200.so — C ABI (include/diamond_b200.h) over the sm_100a kernels.
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <map>
 #include <cuda_runtime.h>
@@ -14,6 +15,8 @@
 #include "../../include/diamond_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_tc.cuh"
+#include "wgrad_tc.cuh"
+#include "bwd_kernels.cuh"
 
 using namespace dmd;
 
@@ -151,22 +154,39 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   return 0;
 }
 
-static int g_num_sms = 0;
-static int init_kernels() {  // opt in to >48 KB dynamic shared memory once (never during stream capture)
-  static bool done = false;
-  if (done) return 0;
+// Per-device state: SM count, the >48 KB dynamic shared memory opt-ins (function attributes are per device) and a small
+// all-zero buffer (source of the zero row groups of the wgrad kernel).  Initialised on first use of each device, never
+// during stream capture.
+struct DevState { int num_sms = 0; void* zeros = nullptr; };
+static thread_local int g_num_sms = 0;
+static thread_local const uint8_t* g_zeros = nullptr;
+static int init_kernels() {
+  static std::mutex mu;
+  static std::map<int, DevState> states;
   int dev = 0;
   DMD_CUDA(cudaGetDevice(&dev));
-  DMD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  DMD_CUDA(cudaFuncSetAttribute(linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  done = true;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = states.find(dev);
+  if (it == states.end()) {
+    DevState st;
+    DMD_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    DMD_CUDA(cudaMalloc(&st.zeros, 4096));
+    DMD_CUDA(cudaMemset(st.zeros, 0, 4096));
+    it = states.emplace(dev, st).first;
+  }
+  g_num_sms = it->second.num_sms;
+  g_zeros = (const uint8_t*)it->second.zeros;
   return 0;
 }
 
@@ -218,7 +238,8 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
     if (d->mode == 2) DMD_CHECK(d->gamma && d->beta, "prep: GroupNorm needs gamma/beta");
     DMD_CHECK(d->upsample == 0, "prep: norm + upsample unsupported");
   }
-  p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample ? 1 : 0;
+  p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample;   // 1 nearest-2x, 2 zero insertion (stride-2 adjoint)
+  DMD_CHECK(d->upsample >= 0 && d->upsample <= 2, "prep: upsample must be 0, 1 (nearest 2x) or 2 (zero insertion)");
   p->H = d->upsample ? 2 * d->Hs : d->Hs; p->W = d->upsample ? 2 * d->Ws : d->Ws;
   p->mode = d->mode; p->act = d->silu ? 1 : 0;
   p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off; p->film_ctot = d->C0 + d->C1;
@@ -273,6 +294,94 @@ extern "C" int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream) {
   ConvParams p; size_t smem; int cols;
   if (conv_fill(d, &p, &smem, &cols)) return 1;
   return conv_launch(p, smem, cols, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad launcher
+// Fills the tcgen05 weight-gradient launch for one (gradient operand, activation operand) pair.  grad: PLC16, Cg stored
+// channels (<= 64); act: PLC16, Ca stored channels (16 / 32 / 64), both over B images of H x W (conv INPUT size; a
+// stride-2 conv passes its zero-inserted gradient).
+struct WgradLaunch { WgradParams wp; WgradReduceParams rp; size_t smem; int grid; };
+static size_t wgrad_partial_bytes(int num_sms) { return (size_t)num_sms * kWgMaxMma * kTileM * 64 * sizeof(float); }
+
+static int wgrad_fill(const void* grad, int Cg, const void* act, int Ca, int B, int H, int W, int taps, float* partial,
+                      int Cout, int Cin, int CinTot, int ci_off, const float* inv_scale, int accumulate, int debug, WgradLaunch* L) {
+  DMD_CHECK(grad && act && partial, "wgrad: null operand / partial buffer");
+  DMD_CHECK(taps == 9 || taps == 1, "wgrad: taps must be 1 or 9");
+  DMD_CHECK(Cg % 8 == 0 && Cg > 0 && Cg <= 64, "wgrad: gradient operand channels must be a multiple of 8, <= 64 (got %d)", Cg);
+  DMD_CHECK(Ca == 16 || Ca == 32 || Ca == 64, "wgrad: activation operand channels must be 16, 32 or 64 (got %d)", Ca);
+  DMD_CHECK(Cout > 0 && Cout <= Cg && Cin > 0 && Cin <= Ca && ci_off >= 0 && ci_off + Cin <= CinTot, "wgrad: bad channel counts");
+  if (init_kernels()) return 1;
+  memset(L, 0, sizeof(*L));
+  const Plc g = plc_geometry(B, H, W);
+  const size_t plane = (size_t)g.Qalloc * 16;
+  WgradParams& wp = L->wp;
+  const int ng = Cg / 8;
+  for (int k = 0; k < 16; ++k) {
+    const int j = k & 7;
+    const bool second = k >= 8;
+    wp.a_plane[k] = (j < ng && !(second && taps == 1)) ? (const uint8_t*)grad + (size_t)j * plane : nullptr;
+    wp.a_shift[k] = second ? -g.PW : 0;
+  }
+  wp.zeros = g_zeros;
+  wp.nB = Ca / 8;
+  for (int j = 0; j < wp.nB; ++j) wp.b_plane[j] = (const uint8_t*)act + (size_t)j * plane;
+  WgradReduceParams& rp = L->rp;
+  for (int i = 0; i < kWgMaxMma; ++i) rp.tap_of[i][0] = rp.tap_of[i][1] = -1;
+  if (taps == 9) {
+    wp.n_mma = 6; wp.halo = g.PW + 1;
+    for (int i = 0; i < 3; ++i) {
+      wp.b_shift[i] = -g.PW - 1 + i;      // rows 0-63: tap (ky = 0, kx = i); rows 64-127 (window shifted by -PW): tap (1, i)
+      rp.tap_of[i][0] = i; rp.tap_of[i][1] = 3 + i;
+      wp.b_shift[3 + i] = g.PW - 1 + i;   // rows 0-63: tap (2, i); rows 64-127 unused
+      rp.tap_of[3 + i][0] = 6 + i;
+    }
+  } else {
+    wp.n_mma = 1; wp.halo = 0; wp.b_shift[0] = 0; rp.tap_of[0][0] = 0;
+  }
+  wp.G = g.G; wp.num_tiles = (g.Q + kTileM - 1) / kTileM; wp.Pb = kTileM + 2 * wp.halo;
+  const WgradSmem one = wgrad_smem(wp.nB, wp.halo, 1);
+  int stages = (int)((227ll * 1024 - 512) / (long long)(one.a_bytes + one.b_bytes));
+  if (stages > kWgStagesMax) stages = kWgStagesMax;
+  DMD_CHECK(stages >= 2, "wgrad: image too wide for the shared-memory stage (W=%d)", W);
+  wp.stages = stages;
+  wp.partial = partial; wp.dbg = debug;
+  L->smem = wgrad_smem(wp.nB, wp.halo, stages).total;
+  L->grid = wp.num_tiles < g_num_sms ? wp.num_tiles : g_num_sms;
+  rp.partial = partial; rp.nparts = L->grid; rp.n_mma = wp.n_mma; rp.N = Ca;
+  rp.Cout = Cout; rp.Cin = Cin; rp.CinTot = CinTot; rp.ci_off = ci_off; rp.taps = taps;
+  rp.inv_scale = inv_scale; rp.accumulate = accumulate;
+  return 0;
+}
+static int wgrad_launch(const WgradLaunch& L, float* dW, cudaStream_t st) {
+  if (launch_pdl(wgrad_tc_kernel, dim3(L.grid), dim3(kWgThreads), L.smem, st, L.wp)) return 1;
+  WgradReduceParams rp = L.rp;
+  rp.dW = dW;
+  const int total = rp.n_mma * 2 * 64 * rp.N;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(rp);
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t dmd_wgrad_partial_bytes(void) {
+  if (init_kernels()) return 0;
+  return wgrad_partial_bytes(g_num_sms);
+}
+extern "C" int dmd_conv2d_wgrad(const dmd_wgrad_desc* d, void* stream) {
+  DMD_CHECK(d && d->dW, "wgrad: null descriptor / dW");
+  if (init_kernels()) return 1;
+  DMD_CHECK(d->partial_bytes >= wgrad_partial_bytes(g_num_sms), "wgrad: partial buffer too small (%zu < %zu)", d->partial_bytes, wgrad_partial_bytes(g_num_sms));
+  WgradLaunch L;
+  if (wgrad_fill(d->grad, d->Cg, d->act, d->Ca, d->B, d->H, d->W, d->taps, (float*)d->partial, d->Cout, d->Cin, d->CinTot, d->ci_off,
+                 d->inv_scale, d->accumulate, d->debug, &L)) return 1;
+  return wgrad_launch(L, d->dW, (cudaStream_t)stream);
+}
+extern "C" int dmd_pack_conv_weight_dgrad(const float* w, void* wpk, int CoutF, int CinTotF, int ci_off, int CinK, int taps, void* stream) {
+  DMD_CHECK(w && wpk, "pack_T: null pointer");
+  const int CinP = round_up(CoutF, 16), CoutP = round_up(CinK, 16);
+  const int total = taps * CinP * CoutP;
+  pack_conv_weight_T_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, CoutF, CinTotF, ci_off, CinK, CinP, CoutP, taps);
+  DMD_LAUNCH_OK();
+  return 0;
 }
 
 extern "C" int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
@@ -352,6 +461,8 @@ struct ConvW {          // one nn.Conv2d
   int Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store;
   int precise = 0;      // split-fp16: K = 3 * Cin
   size_t pk_off;        // byte offset into the packed-weight buffer
+  // backward-data packs (transposed, tap-flipped; one per source of a channel concat), training only
+  int nsrcT = 0; int srcC[2] = {0, 0}; int srcOff[2] = {0, 0}; size_t pkT_off[2] = {0, 0};
 };
 struct FilmW { int w_idx, b_idx, C, off; };  // AdaGroupNorm.linear ; off = row offset into the batched FiLM GEMM
 struct ResBlockW {
@@ -361,11 +472,42 @@ struct ResBlockW {
   int has_attn; int an_w, an_b, qkv_w, qkv_b, op_w, op_b;
 };
 
-struct Tens { float* data; double* stats; int C, H, W, gs; };
+struct Tens { float* data; double* stats; int C, H, W, gs; float* grad = nullptr; int gid = -1; };
 
 enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2 };
 struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; };
 constexpr int kScratchSlots = 10;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
+
+// PLC16 operands produced by one prep launch (op = index of that launch in Plan::ops, replayed by the backward pass)
+struct Operand { uint8_t *n0 = nullptr, *n1 = nullptr, *r0 = nullptr, *r1 = nullptr, *nl0 = nullptr, *rl0 = nullptr, *rl1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0, op = -1; };
+
+// backward op list (training).  Parameter-gradient destinations are OFFSETS into the caller's flat gradient buffer.
+enum BKind { B_PREP = 0, B_CONV, B_WGRAD, B_COLSUM, B_NORM1, B_NORM2, B_AFFINE, B_POOL, B_ADD, B_ATTN, B_MEMSET, B_SGEMM, B_FILMW,
+             B_LINEAR, B_DSILU, B_EMB };
+struct BOp {
+  int kind = 0;
+  PrepParams prep; int prep_nsrc = 1;
+  ConvParams conv; size_t smem = 0; int cols = 0;
+  WgradLaunch wg;
+  long long goff = -1, goff2 = -1;            // flat-gradient offsets (floats)
+  NormBwdParams nb; int ppb = 0, chunks = 0;
+  const float* src = nullptr; float* dst = nullptr; long long rows = 0; int C = 0, Creal = 0, H = 0, W = 0, acc = 0; long long total4 = 0;
+  AttnBwdParams ab; long long goffs[6] = {-1, -1, -1, -1, -1, -1};
+  void* ms_ptr = nullptr; size_t ms_bytes = 0;
+  // sgemm: C = alpha * op(A) op(B); c_goff >= 0 -> C lives in the gradient buffer
+  const float *ga = nullptr, *gb = nullptr; float* gc = nullptr; long long sam = 0, sak = 0, sbk = 0, sbn = 0, ldc = 0, c_goff = -1;
+  int M = 0, N = 0, K = 0, use_inv = 0;
+  // linear recompute
+  const float *lin_in = nullptr, *lin_w = nullptr, *lin_b = nullptr; float* lin_out = nullptr; int lin_K = 0, lin_F = 0;
+};
+
+enum RecKind { R_CONVIN = 0, R_DOWN, R_UP, R_RES, R_OUT };
+struct Rec {
+  int kind = 0;
+  const ConvW* cw = nullptr; const ResBlockW* rb = nullptr;
+  Tens x, skip, t, o, a; bool has_skip = false;
+  Operand in1, in2;
+};
 
 struct Plan {
   int B = 0, H = 0, W = 0;
@@ -377,18 +519,35 @@ struct Plan {
   std::vector<Op> ops;
   uint8_t* scratch[kScratchSlots] = {nullptr};
   int scratch_next = 0;
-  // sampler state (NCHW fp32)
-  float *s_obs = nullptr, *s_x[2] = {nullptr, nullptr}, *s_x2 = nullptr, *s_d = nullptr, *s_traj = nullptr, *s_eps = nullptr;
-  int64_t* s_act = nullptr;
+  // training (dmd_inner_model_forward_train / dmd_denoiser_backward): gradient buffers and the backward op list
+  bool train = false;
+  int n_grad_tensors = 0;
+  std::vector<BOp> bops;
+  std::vector<Rec> tape;
+  const int64_t* t_act = nullptr;                         // the forward's action tensor (embedding gradient)
+  float *tA = nullptr, *tB = nullptr, *tC = nullptr;      // fp32 NHWC temporaries (largest activation)
+  uint8_t *gyA = nullptr, *gyB = nullptr;                 // PLC16 gradient operands
+  float *gF = nullptr;                                    // scaled dL/d(model output), NHWC with 8 channels
+  float *dfilm = nullptr, *nsum = nullptr, *partial = nullptr, *scale = nullptr;
+  float *dcond = nullptr, *dh = nullptr, *cpre = nullptr, *dpre = nullptr, *de = nullptr;
+  unsigned int* amax = nullptr;
+  long long *film_woff = nullptr, *film_boff = nullptr;   // device tables: flat-gradient offset of every FiLM row
+  std::vector<long long> film_woff_h, film_boff_h;
+  uint8_t* zero_begin = nullptr; size_t zero_bytes = 0;   // region cleared at the start of every backward (dfilm, sums, amax)
+  // sampler state (NCHW fp32): temporaries only -- the frame stack, the actions and the trajectory are used IN PLACE
+  float *s_xc = nullptr, *s_x2 = nullptr, *s_d = nullptr;
+  float *sig_all = nullptr, *cemb_all = nullptr, *chid_all = nullptr, *cond_all = nullptr, *film_all = nullptr;  // hoisted conditioning
 };
 
+constexpr int kMaxSamplerEvals = 24;   // U-Net evaluations per sample() whose conditioning is hoisted (12 Heun / 24 Euler steps)
 struct SamplerGraph {
   bool valid = false;
   int B = 0, H = 0, W = 0; void* ws = nullptr; int order = 0; bool has_eps = false;
+  const void *obs = nullptr, *act = nullptr, *traj = nullptr, *eps = nullptr, *out = nullptr; StackView sv{};   // graphs bake pointers in
+  unsigned long long stamp = 0;
   std::vector<float> sigmas; float churn[4] = {0, 0, 0, 0};
   long long kernels = 0;  // kernel nodes per replay
   cudaGraphExec_t exec = nullptr;
-  cudaStream_t cap_stream = nullptr;  // capture never happens on the caller's stream (torch's default is the legacy stream)
 };
 
 }  // namespace
@@ -406,8 +565,15 @@ struct dmd_denoiser {
   size_t packed_bytes = 0, film_w_off = 0, film_b_off = 0;
   std::vector<const float*> ptrs;
   uint8_t* packed = nullptr;
+  std::vector<long long> numel, goff;   // per state_dict tensor: element count and offset into the flat gradient buffer
+  long long grad_total = 0;
   Plan plan;
-  SamplerGraph graph;
+  std::vector<SamplerGraph> graphs;     // one per distinct (buffers, ring head): a WorldModelEnv replays T of them round-robin
+  unsigned long long graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  // training plans, one per live training workspace (an autoregressive Denoiser.forward holds several forwards before
+  // their backwards run); kept apart from `plan` so that imagination and training can alternate
+  std::vector<std::unique_ptr<Plan>> tplans;
   int need_B = 0, need_H = 0, need_W = 0; size_t need_bytes = 0;
 };
 
@@ -415,14 +581,26 @@ namespace {
 
 struct Walker {  // assigns state_dict indices in module registration order and packed-buffer offsets
   dmd_denoiser* h; int idx = 0; size_t pk = 0;
-  ConvW conv(int cout, int cin_real, int taps, int c0_real, int c0_store, int c1, int precise = 0) {
-    ConvW c; c.w_idx = idx++; c.b_idx = idx++;
+  int next(long long n) { h->numel.push_back(n); return idx++; }
+  ConvW conv(int cout, int cin_real, int taps, int c0_real, int c0_store, int c1, int precise = 0, bool dgrad = true) {
+    ConvW c; c.w_idx = next((long long)cout * cin_real * taps); c.b_idx = next(cout);
     c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
     c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16); c.precise = precise;
     c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2 * (precise ? 3 : 1); pk = (pk + 255) & ~(size_t)255;
+    if (dgrad) {
+      c.nsrcT = c1 ? 2 : 1;
+      c.srcC[0] = c0_real; c.srcC[1] = c1; c.srcOff[0] = 0; c.srcOff[1] = c0_real;
+      for (int k = 0; k < c.nsrcT; ++k) {
+        c.pkT_off[k] = pk;
+        pk += (size_t)taps * round_up(cout, 16) * round_up(c.srcC[k], 16) * 2; pk = (pk + 255) & ~(size_t)255;
+      }
+    }
     return c;
   }
-  FilmW film(int C) { FilmW f; f.w_idx = idx++; f.b_idx = idx++; f.C = C; f.off = h->film_rows; h->film_rows += 2 * C; return f; }
+  FilmW film(int C) {
+    FilmW f; f.w_idx = next((long long)2 * C * h->cfg.cond_channels); f.b_idx = next(2 * C);
+    f.C = C; f.off = h->film_rows; h->film_rows += 2 * C; return f;
+  }
   // c0/c1: channels of the two concatenated inputs (c1 = 0: single input)
   ResBlockW resblock(int c0, int c1, int cout, bool attn) {
     ResBlockW r; r.cin = c0 + c1; r.cout = cout;
@@ -433,7 +611,10 @@ struct Walker {  // assigns state_dict indices in module registration order and 
     r.n2 = film(cout);
     r.c2 = conv(cout, cout, 9, cout, cout, 0);
     r.has_attn = attn;
-    if (attn) { r.an_w = idx++; r.an_b = idx++; r.qkv_w = idx++; r.qkv_b = idx++; r.op_w = idx++; r.op_b = idx++; }
+    if (attn) {
+      r.an_w = next(cout); r.an_b = next(cout); r.qkv_w = next((long long)3 * cout * cout); r.qkv_b = next(3 * cout);
+      r.op_w = next((long long)cout * cout); r.op_b = next(cout);
+    }
     return r;
   }
 };
@@ -444,11 +625,13 @@ int build_structure(dmd_denoiser* h) {
   Walker w{h};
   // InnerModel.__init__ registration order (inner_model.py:24-42): noise_emb, act_emb, cond_proj, conv_in, unet,
   // norm_out, conv_out.  UNet (blocks.py:183-220): d_blocks, u_blocks, mid_blocks, downsamples, upsamples.
-  h->i_fourier = w.idx++; h->i_actemb = w.idx++;
-  h->i_cp0w = w.idx++; h->i_cp0b = w.idx++; h->i_cp2w = w.idx++; h->i_cp2b = w.idx++;
+  const long long CC = c.cond_channels;
+  h->numel.clear();
+  h->i_fourier = w.next(CC / 2); h->i_actemb = w.next((long long)c.num_actions * (CC / c.num_steps_conditioning));
+  h->i_cp0w = w.next(CC * CC); h->i_cp0b = w.next(CC); h->i_cp2w = w.next(CC * CC); h->i_cp2b = w.next(CC);
   const int cin_real = (c.num_steps_conditioning + 1) * c.img_channels;
   const int cin_store = round_up(cin_real, 16);
-  h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0, 1);
+  h->conv_in = w.conv(c.channels[0], cin_real, 9, cin_real, cin_store, 0, 1, false);  // its input needs no gradient
   h->d_blocks.resize(L);
   for (int i = 0; i < L; ++i) {
     const int c1 = c.channels[i > 0 ? i - 1 : 0], c2 = c.channels[i];
@@ -469,9 +652,12 @@ int build_structure(dmd_denoiser* h) {
   h->downs.resize(L); h->ups.resize(L);
   for (int i = 1; i < L; ++i) h->downs[i] = w.conv(c.channels[i - 1], c.channels[i - 1], 9, c.channels[i - 1], c.channels[i - 1], 0);
   for (int m = 1; m < L; ++m) { const int ch = c.channels[L - 1 - m]; h->ups[m] = w.conv(ch, ch, 9, ch, ch, 0); }
-  h->i_normout_w = w.idx++; h->i_normout_b = w.idx++;
+  h->i_normout_w = w.next(c.channels[0]); h->i_normout_b = w.next(c.channels[0]);
   h->conv_out = w.conv(c.img_channels, c.channels[0], 9, c.channels[0], c.channels[0], 0, 0);  // split-fp16 here costs 3x on an N=16 conv for 3.2e-4
   h->n_tensors = w.idx;
+  h->goff.assign(h->n_tensors, 0);
+  h->grad_total = 0;
+  for (int i = 0; i < h->n_tensors; ++i) { h->goff[i] = h->grad_total; h->grad_total += (h->numel[i] + 3) & ~3ll; }  // 16-byte aligned slices
   size_t pk = w.pk;
   h->film_w_off = pk; pk += (size_t)h->film_rows * c.cond_channels * 4; pk = (pk + 255) & ~(size_t)255;
   h->film_b_off = pk; pk += (size_t)h->film_rows * 4; pk = (pk + 255) & ~(size_t)255;
@@ -488,16 +674,15 @@ struct Bump {
 struct PlanBuilder {
   dmd_denoiser* h; Plan* pl; Bump* bump; Bump* sbump; int err = 0;
 
-  Tens tensor(int C, int H, int W, bool with_stats) {
+  Tens tensor(int C, int H, int W, bool with_stats, bool with_grad = true) {
     Tens t; t.C = C; t.H = H; t.W = W; t.gs = gn_group_size(C);
     t.data = (float*)bump->take((size_t)pl->B * H * W * C * 4);
     t.stats = with_stats ? (double*)sbump->take((size_t)pl->B * (C / t.gs) * 2 * 8) : nullptr;
+    if (pl->train && with_grad) { t.grad = (float*)bump->take((size_t)pl->B * H * W * C * 4); t.gid = pl->n_grad_tensors++; }
     return t;
   }
+  void record(const Rec& r) { if (pl->train) pl->tape.push_back(r); }
   const float* P(int idx) const { return h->ptrs.empty() ? nullptr : h->ptrs[idx]; }
-
-  // PLC16 operands produced by one prep launch
-  struct Operand { uint8_t *n0 = nullptr, *n1 = nullptr, *r0 = nullptr, *r1 = nullptr, *nl0 = nullptr, *rl0 = nullptr, *rl1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0; };
 
   uint8_t* scratch() {
     uint8_t* p = pl->scratch[pl->scratch_next];
@@ -528,6 +713,7 @@ struct PlanBuilder {
     o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
     Op op; op.kind = OP_PREP;
     if (prep_fill(&d, &op.prep, &op.prep_nsrc)) { err = 1; return o; }
+    o.op = (int)pl->ops.size();
     pl->ops.push_back(op);
     return o;
   }
@@ -559,18 +745,22 @@ struct PlanBuilder {
   Tens resblock(const ResBlockW& rb, const Tens& x, const Tens* skip) {
     const int H = x.H, W = x.W;
     Operand in1 = prep(x, skip, 0, 1, &rb.n1, 0, 0, true, rb.has_proj != 0, rb.has_proj != 0);
-    Tens t = tensor(rb.cout, H, W, true);
+    Tens t = tensor(rb.cout, H, W, true, false);   // its gradient lives in a temporary
     conv(rb.c1, in1, false, 1, nullptr, t, true);
     Operand in2 = prep(t, nullptr, 0, 1, &rb.n2, 0, 0, true, false);
     Tens o = tensor(rb.cout, H, W, true);
     // x + r: r is the block input itself, or proj(input) fused into conv2's accumulator (no r tensor, no extra launch)
     if (rb.has_proj) conv(rb.c2, in2, false, 1, nullptr, o, true, &rb.proj, &in1);
     else conv(rb.c2, in2, false, 1, &x, o, true);
-    if (!rb.has_attn) return o;
+    Rec rec; rec.kind = R_RES; rec.rb = &rb; rec.x = x; rec.has_skip = skip != nullptr; if (skip) rec.skip = *skip;
+    rec.t = t; rec.o = o; rec.in1 = in1; rec.in2 = in2;
+    if (!rb.has_attn) { record(rec); return o; }
     Tens a = tensor(rb.cout, H, W, true);
     Op op; op.kind = OP_ATTN;
     op.attn = AttnParams{o.data, o.stats, P(rb.an_w), P(rb.an_b), P(rb.qkv_w), P(rb.qkv_b), P(rb.op_w), P(rb.op_b), a.data, a.stats, H * W, rb.cout, o.gs, kGnEps};
     pl->ops.push_back(op);
+    rec.a = a;
+    record(rec);
     return a;
   }
 
@@ -594,13 +784,19 @@ struct PlanBuilder {
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
     Tens x = tensor(c.channels[0], H, W, true);
-    conv(h->conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true), false, 1, nullptr, x, true);
+    {
+      Operand in = prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true);
+      conv(h->conv_in, in, false, 1, nullptr, x, true);
+      Rec rec; rec.kind = R_CONVIN; rec.cw = &h->conv_in; rec.x = xin; rec.o = x; rec.in1 = in; record(rec);
+    }
     std::vector<std::vector<Tens>> d_outputs;
     for (int i = 0; i < L; ++i) {
       Tens xd = x;
       if (i > 0) {  // Downsample (blocks.py:93-100): raw input, stride 2
         xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true);
-        conv(h->downs[i], prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 2, nullptr, xd, true);
+        Operand in = prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false);
+        conv(h->downs[i], in, false, 2, nullptr, xd, true);
+        Rec rec; rec.kind = R_DOWN; rec.cw = &h->downs[i]; rec.x = x; rec.o = xd; rec.in1 = in; record(rec);
       }
       std::vector<Tens> outs{xd};
       x = xd;
@@ -612,7 +808,9 @@ struct PlanBuilder {
       Tens xu = x;
       if (m > 0) {  // Upsample (blocks.py:103-110): nearest x2 folded into the operand, then conv
         xu = tensor(x.C, x.H * 2, x.W * 2, true);
-        conv(h->ups[m], prep(x, nullptr, 1, 0, nullptr, 0, 0, false, false), false, 1, nullptr, xu, true);
+        Operand in = prep(x, nullptr, 1, 0, nullptr, 0, 0, false, false);
+        conv(h->ups[m], in, false, 1, nullptr, xu, true);
+        Rec rec; rec.kind = R_UP; rec.cw = &h->ups[m]; rec.x = x; rec.o = xu; rec.in1 = in; record(rec);
       }
       x = xu;
       const std::vector<Tens>& skip = d_outputs[L - 1 - m];  // reversed(d_outputs); block k uses skip[::-1][k]
@@ -623,13 +821,20 @@ struct PlanBuilder {
     pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
     Tens f{pl->fout, nullptr, pl->CF, H, W, pl->CF};
     // conv_out(silu(norm_out(x)))  (inner_model.py:48)
-    conv(h->conv_out, prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false, false), false, 1, nullptr, f, false);
-    // sampler buffers
+    {
+      Operand in = prep(x, nullptr, 0, 2, nullptr, h->i_normout_w, h->i_normout_b, true, false, false);
+      conv(h->conv_out, in, false, 1, nullptr, f, false);
+      Rec rec; rec.kind = R_OUT; rec.cw = &h->conv_out; rec.x = x; rec.in1 = in; record(rec);
+    }
+    // sampler temporaries + hoisted conditioning of up to kMaxSamplerEvals evaluations
     const size_t img = (size_t)B * c.img_channels * H * W * 4;
-    pl->s_obs = (float*)bump->take(img * c.num_steps_conditioning);
-    pl->s_act = (int64_t*)bump->take((size_t)B * c.num_steps_conditioning * 8);
-    pl->s_x[0] = (float*)bump->take(img); pl->s_x[1] = (float*)bump->take(img);
-    pl->s_x2 = (float*)bump->take(img); pl->s_d = (float*)bump->take(img);
+    pl->s_xc = (float*)bump->take(img); pl->s_x2 = (float*)bump->take(img); pl->s_d = (float*)bump->take(img);
+    if (!pl->train) {
+      const size_t K = kMaxSamplerEvals;
+      pl->sig_all = (float*)bump->take(K * 4);
+      pl->cemb_all = (float*)bump->take(K * B * c.cond_channels * 4); pl->chid_all = (float*)bump->take(K * B * c.cond_channels * 4);
+      pl->cond_all = (float*)bump->take(K * B * c.cond_channels * 4); pl->film_all = (float*)bump->take(K * B * h->film_rows * 4);
+    }
     return err;
   }
 };
@@ -650,28 +855,274 @@ int make_plan(dmd_denoiser* h, Plan* pl, int B, int H, int W, uint8_t* base, siz
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- backward plan (training)
+// Walks the forward tape in reverse and emits the backward op list.  Every gradient tensor is fp32 NHWC and carries the
+// loss scale; "first writer assigns, later writers accumulate" is decided here at plan time (ginit), so no gradient
+// buffer needs a memset.  Forward conv inputs (the PLC16 operands) are not kept: the forward prep launch is replayed.
+struct BwdBuilder {
+  dmd_denoiser* h; Plan* pl; Bump* bump; int err = 0;
+  std::vector<char> ginit;
+
+  const float* P(int idx) const { return h->ptrs.empty() ? nullptr : h->ptrs[idx]; }
+  bool was_init(const Tens& t) { const bool w = ginit[t.gid] != 0; ginit[t.gid] = 1; return w; }
+  void push(const BOp& b) { pl->bops.push_back(b); }
+
+  void replay(const Operand& o) { BOp b; b.kind = B_PREP; b.prep = pl->ops[o.op].prep; b.prep_nsrc = pl->ops[o.op].prep_nsrc; push(b); }
+  // NHWC fp32 gradient [B][Hs][Ws][C] -> PLC16 operand (ups = 2: zero insertion, the adjoint of a stride-2 conv)
+  void gprep(const float* g, int C, int Hs, int Ws, int ups, uint8_t* dst) {
+    dmd_prep_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = g ? g : (const float*)1; d.C0 = C; d.B = pl->B; d.Hs = Hs; d.Ws = Ws; d.upsample = ups; d.dst0 = dst ? dst : (void*)1; d.eps = kGnEps;
+    BOp b; b.kind = B_PREP;
+    if (prep_fill(&d, &b.prep, &b.prep_nsrc)) { err = 1; return; }
+    push(b);
+  }
+  void colsum(const float* g, long long rows, int C, int Creal, int idx, int idx2 = -1) {
+    BOp b; b.kind = B_COLSUM; b.src = g; b.rows = rows; b.C = C; b.Creal = Creal; b.goff = h->goff[idx]; b.goff2 = idx2 >= 0 ? h->goff[idx2] : -1;
+    push(b);
+  }
+  // backward-data for source k of conv cw: out (+)= conv(gy, W_k^T flipped)
+  void dgrad(const ConvW& cw, int k, const uint8_t* gy, int H, int W, float* out, bool accumulate) {
+    dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = gy ? gy : (const void*)1; d.C0 = round_up(cw.Cout, 16); d.B = pl->B; d.H = H; d.W = W; d.taps = cw.taps; d.stride = 1;
+    d.wpk = h->packed ? h->packed + cw.pkT_off[k] : (const void*)1;
+    d.Cout = cw.srcC[k]; d.CoutPad = round_up(cw.srcC[k], 16);
+    d.out = out ? out : (float*)1; d.residual = accumulate ? d.out : nullptr;
+    BOp b; b.kind = B_CONV;
+    if (conv_fill(&d, &b.conv, &b.smem, &b.cols)) { err = 1; return; }
+    push(b);
+  }
+  void wgrad(const ConvW& cw, const uint8_t* gy, const uint8_t* act, int Ca, int Cin, int ci_off, int H, int W) {
+    BOp b; b.kind = B_WGRAD; b.goff = h->goff[cw.w_idx];
+    if (wgrad_fill(gy ? gy : (const void*)1, round_up(cw.Cout, 16), act ? act : (const void*)1, Ca, pl->B, H, W, cw.taps,
+                   pl->partial ? pl->partial : (float*)1, cw.Cout, Cin, cw.CinReal, ci_off, pl->scale ? pl->scale + 1 : (const float*)1, 1, 0, &b.wg)) { err = 1; return; }
+    push(b);
+  }
+  void norm_bwd(const Tens& x, const float* gy, int mode, const FilmW* film, int c_off, int ctot, int gamma_idx, int beta_idx,
+                float* gx, const float* addend, bool accumulate) {
+    NormBwdParams nb; memset(&nb, 0, sizeof(nb));
+    nb.x = x.data; nb.gy = gy; nb.stats = x.stats; nb.B = pl->B; nb.HW = x.H * x.W; nb.C = x.C; nb.gs = x.gs; nb.mode = mode; nb.act = 1;
+    nb.eps = kGnEps; nb.c_off = c_off;
+    BOp b1; b1.kind = B_NORM1;
+    if (mode == 1) {
+      nb.film = pl->film; nb.film_stride = h->film_rows; nb.film_off = film->off; nb.film_ctot = ctot;
+      nb.sumB = pl->dfilm ? pl->dfilm + film->off + c_off : nullptr;            // d scale
+      nb.sumA = pl->dfilm ? pl->dfilm + film->off + ctot + c_off : nullptr;     // d shift
+      nb.sum_stride = h->film_rows;
+    } else {
+      nb.gamma = P(gamma_idx); nb.beta = P(beta_idx);
+      nb.sumA = pl->nsum; nb.sumB = pl->nsum ? pl->nsum + (size_t)pl->B * kMaxCin : nullptr; nb.sum_stride = kMaxCin;
+      BOp m; m.kind = B_MEMSET; m.ms_ptr = pl->nsum; m.ms_bytes = (size_t)2 * pl->B * kMaxCin * 4; push(m);
+    }
+    nb.gx = gx; nb.addend = addend; nb.accumulate = accumulate ? 1 : 0;
+    // pixels per block: enough blocks to cover the SMs, at least 32 pixels each
+    int ppb = nb.HW;
+    while (ppb > 32 && (long long)pl->B * ((nb.HW + ppb - 1) / ppb) < 2 * 148) ppb >>= 1;
+    b1.nb = nb; b1.ppb = ppb; b1.chunks = (nb.HW + ppb - 1) / ppb;
+    push(b1);
+    if (mode == 2) {
+      BOp a; a.kind = B_AFFINE; a.nb = nb; a.goff = h->goff[gamma_idx]; a.goff2 = h->goff[beta_idx]; push(a);
+    }
+    BOp b2 = b1; b2.kind = B_NORM2; push(b2);
+  }
+
+  // ResBlock.forward (blocks.py:141-147) backward
+  void resblock(const Rec& r) {
+    const ResBlockW& rb = *r.rb;
+    const int H = r.o.H, W = r.o.W, B = pl->B;
+    const long long pix = (long long)B * H * W;
+    Tens o = r.o;
+    if (rb.has_attn) {  // attention consumes o alone: its backward ASSIGNS o's gradient
+      BOp b; b.kind = B_ATTN;
+      b.ab = AttnBwdParams{o.data, o.stats, P(rb.an_w), P(rb.an_b), P(rb.qkv_w), P(rb.qkv_b), P(rb.op_w), r.a.grad, o.grad,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pl->scale ? pl->scale + 1 : nullptr, H * W, rb.cout, o.gs, kGnEps};
+      const int ids[6] = {rb.an_w, rb.an_b, rb.qkv_w, rb.qkv_b, rb.op_w, rb.op_b};
+      for (int i = 0; i < 6; ++i) b.goffs[i] = h->goff[ids[i]];
+      push(b);
+      ginit[o.gid] = 1;
+    }
+    const Tens* src[2] = {&r.x, r.has_skip ? &r.skip : nullptr};
+    const int nsrc = r.has_skip ? 2 : 1;
+    // ---- conv2 (+ fused projection): gradient operand of o
+    gprep(o.grad, rb.cout, H, W, 0, pl->gyA);
+    colsum(o.grad, pix, rb.cout, rb.cout, rb.c2.b_idx, rb.has_proj ? rb.proj.b_idx : -1);
+    replay(r.in2);
+    wgrad(rb.c2, pl->gyA, r.in2.n0, round_up(rb.cout, 16), rb.cout, 0, H, W);
+    dgrad(rb.c2, 0, pl->gyA, H, W, pl->tA, false);
+    // ---- norm2 + SiLU
+    norm_bwd(r.t, pl->tA, 1, &rb.n2, 0, rb.cout, 0, 0, pl->tB, nullptr, false);
+    // ---- conv1
+    gprep(pl->tB, rb.cout, H, W, 0, pl->gyB);
+    colsum(pl->tB, pix, rb.cout, rb.cout, rb.c1.b_idx);
+    replay(r.in1);
+    for (int k = 0; k < nsrc; ++k) {
+      const uint8_t* act = k == 0 ? r.in1.n0 : r.in1.n1;
+      wgrad(rb.c1, pl->gyB, act, round_up(src[k]->C, 16), src[k]->C, rb.c1.srcOff[k], H, W);
+      float* ga = k == 0 ? pl->tA : pl->tC;
+      dgrad(rb.c1, k, pl->gyB, H, W, ga, false);
+      // ---- norm1 + SiLU ; the identity residual (no projection) rides along as the addend of source 0
+      const float* addend = (!rb.has_proj && k == 0) ? o.grad : nullptr;
+      const bool acc = was_init(*src[k]);
+      norm_bwd(*src[k], ga, 1, &rb.n1, rb.c1.srcOff[k], rb.cin, 0, 0, src[k]->grad, addend, acc);
+    }
+    if (rb.has_proj) {  // r = proj(cat(x, skip)) (blocks.py:142): 1x1 on the raw operand
+      for (int k = 0; k < nsrc; ++k) {
+        const uint8_t* raw = k == 0 ? r.in1.r0 : r.in1.r1;
+        wgrad(rb.proj, pl->gyA, raw, round_up(src[k]->C, 16), src[k]->C, rb.proj.srcOff[k], H, W);
+        dgrad(rb.proj, k, pl->gyA, H, W, src[k]->grad, true);
+      }
+    }
+  }
+
+  int build() {
+    const int B = pl->B;
+    ginit.assign(pl->n_grad_tensors, 0);
+    pl->bops.clear();
+    for (int i = (int)pl->tape.size() - 1; i >= 0; --i) {
+      const Rec& r = pl->tape[i];
+      if (r.kind == R_OUT) {
+        // conv_out(silu(norm_out(x))) (inner_model.py:48): gF is the scaled gradient of the model output, NHWC x 8 channels
+        const ConvW& cw = *r.cw;
+        const int H = r.x.H, W = r.x.W;
+        gprep(pl->gF, 8, H, W, 0, pl->gyA);
+        colsum(pl->gF, (long long)B * H * W, 8, cw.Cout, cw.b_idx);
+        replay(r.in1);
+        wgrad(cw, pl->gyA, r.in1.n0, round_up(r.x.C, 16), r.x.C, 0, H, W);
+        dgrad(cw, 0, pl->gyA, H, W, pl->tA, false);
+        norm_bwd(r.x, pl->tA, 2, nullptr, 0, r.x.C, h->i_normout_w, h->i_normout_b, r.x.grad, nullptr, was_init(r.x));
+      } else if (r.kind == R_RES) {
+        resblock(r);
+      } else if (r.kind == R_UP) {   // Upsample (blocks.py:103-110): nearest x2 then conv
+        const ConvW& cw = *r.cw;
+        const int H = r.o.H, W = r.o.W;
+        gprep(r.o.grad, cw.Cout, H, W, 0, pl->gyA);
+        colsum(r.o.grad, (long long)B * H * W, cw.Cout, cw.Cout, cw.b_idx);
+        replay(r.in1);
+        wgrad(cw, pl->gyA, r.in1.n0, round_up(r.x.C, 16), r.x.C, 0, H, W);
+        dgrad(cw, 0, pl->gyA, H, W, pl->tA, false);
+        BOp b; b.kind = B_POOL; b.src = pl->tA; b.dst = r.x.grad; b.H = r.x.H; b.W = r.x.W; b.C = r.x.C; b.acc = was_init(r.x) ? 1 : 0;
+        b.total4 = (long long)B * r.x.H * r.x.W * r.x.C / 4;
+        push(b);
+      } else if (r.kind == R_DOWN) {  // Downsample (blocks.py:93-100): stride-2 conv == stride-1 conv sampled at even pixels
+        const ConvW& cw = *r.cw;
+        const int H = r.x.H, W = r.x.W;
+        gprep(r.o.grad, cw.Cout, r.o.H, r.o.W, 2, pl->gyA);
+        colsum(r.o.grad, (long long)B * r.o.H * r.o.W, cw.Cout, cw.Cout, cw.b_idx);
+        replay(r.in1);
+        wgrad(cw, pl->gyA, r.in1.n0, round_up(r.x.C, 16), r.x.C, 0, H, W);
+        dgrad(cw, 0, pl->gyA, H, W, r.x.grad, was_init(r.x));
+      } else {  // R_CONVIN: weight / bias gradients only (the network input needs none)
+        const ConvW& cw = *r.cw;
+        const int H = r.o.H, W = r.o.W;
+        gprep(r.o.grad, cw.Cout, H, W, 0, pl->gyA);
+        colsum(r.o.grad, (long long)B * H * W, cw.Cout, cw.Cout, cw.b_idx);
+        replay(r.in1);
+        wgrad(cw, pl->gyA, r.in1.n0, cw.c0_store, cw.c0_real, 0, H, W);
+      }
+      if (err) return 1;
+    }
+    // ---- conditioning path (inner_model.py:45; blocks.py:39): FiLM linears, cond_proj MLP, action embedding
+    const dmd_denoiser_config& c = h->cfg;
+    const int CC = c.cond_channels, R = h->film_rows;
+    { BOp b; b.kind = B_FILMW; push(b); }
+    auto sgemm = [&](const float* A, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long c_goff,
+                     long long ldc, int M, int N, int K, int use_inv, int acc) {
+      BOp b; b.kind = B_SGEMM; b.ga = A; b.sam = sam; b.sak = sak; b.gb = Bm; b.sbk = sbk; b.sbn = sbn; b.gc = C; b.c_goff = c_goff; b.ldc = ldc;
+      b.M = M; b.N = N; b.K = K; b.use_inv = use_inv; b.acc = acc; push(b);
+    };
+    const float* Wf = h->packed ? (const float*)(h->packed + h->film_w_off) : nullptr;
+    sgemm(pl->dfilm, R, 1, Wf, CC, 1, pl->dcond, -1, CC, B, CC, R, 0, 0);                       // dcond = dfilm Wf
+    sgemm(pl->dcond, 1, CC, pl->chid, CC, 1, nullptr, h->goff[h->i_cp2w], CC, CC, CC, B, 1, 1);  // dW2 += dcond^T h
+    colsum(pl->dcond, B, CC, CC, h->i_cp2b);
+    sgemm(pl->dcond, CC, 1, P(h->i_cp2w), CC, 1, pl->dh, -1, CC, B, CC, CC, 0, 0);               // dh = dcond W2
+    { BOp b; b.kind = B_LINEAR; b.lin_in = pl->cemb; b.lin_w = P(h->i_cp0w); b.lin_b = P(h->i_cp0b); b.lin_out = pl->cpre; b.lin_K = CC; b.lin_F = CC; push(b); }
+    { BOp b; b.kind = B_DSILU; b.src = pl->cpre; b.ga = pl->dh; b.dst = pl->dpre; b.rows = (long long)B * CC; push(b); }
+    sgemm(pl->dpre, 1, CC, pl->cemb, CC, 1, nullptr, h->goff[h->i_cp0w], CC, CC, CC, B, 1, 1);   // dW0 += dpre^T e
+    colsum(pl->dpre, B, CC, CC, h->i_cp0b);
+    sgemm(pl->dpre, CC, 1, P(h->i_cp0w), CC, 1, pl->de, -1, CC, B, CC, CC, 0, 0);                // de = dpre W0
+    { BOp b; b.kind = B_EMB; b.src = pl->de; b.goff = h->goff[h->i_actemb]; push(b); }
+    return err;
+  }
+};
+
+// training workspace = forward plan (with gradient buffers) + backward temporaries
+int make_train_plan(dmd_denoiser* h, Plan* pl, int B, int H, int W, uint8_t* base, size_t* total) {
+  pl->train = true; pl->n_grad_tensors = 0; pl->tape.clear();
+  pl->B = B; pl->H = H; pl->W = W; pl->ops.clear(); pl->bops.clear();
+  Bump b0{nullptr}, s0{nullptr};
+  { Plan tmp; tmp.train = true; tmp.B = B; tmp.H = H; tmp.W = W; PlanBuilder pb{h, &tmp, &b0, &s0}; if (pb.build()) return 1; }
+  const size_t stats_bytes = (s0.off + 255) & ~(size_t)255;
+  Bump sb{base}, bb{base ? base + stats_bytes : nullptr};
+  if (base) { pl->base = base; pl->stats = (double*)base; pl->stats_bytes = stats_bytes; }
+  if (base) { PlanBuilder pb{h, pl, &bb, &sb}; if (pb.build()) return 1; } else bb.off = b0.off;
+  // backward temporaries
+  const dmd_denoiser_config& c = h->cfg;
+  int cmax = 16;
+  for (int i = 0; i < c.num_levels; ++i) cmax = c.channels[i] > cmax ? c.channels[i] : cmax;
+  const size_t act_bytes = (size_t)B * H * W * cmax * 4;
+  pl->tA = (float*)bb.take(act_bytes); pl->tB = (float*)bb.take(act_bytes); pl->tC = (float*)bb.take(act_bytes);
+  const size_t op_bytes = plc16_bytes(B, H, W, cmax);
+  pl->gyA = (uint8_t*)bb.take(op_bytes); pl->gyB = (uint8_t*)bb.take(op_bytes);
+  pl->gF = (float*)bb.take((size_t)B * H * W * 8 * 4);
+  if (init_kernels()) return 1;
+  pl->partial = (float*)bb.take(wgrad_partial_bytes(g_num_sms));
+  const int CC = c.cond_channels;
+  pl->dcond = (float*)bb.take((size_t)B * CC * 4); pl->dh = (float*)bb.take((size_t)B * CC * 4); pl->cpre = (float*)bb.take((size_t)B * CC * 4);
+  pl->dpre = (float*)bb.take((size_t)B * CC * 4); pl->de = (float*)bb.take((size_t)B * CC * 4);
+  pl->film_woff = (long long*)bb.take((size_t)h->film_rows * 8); pl->film_boff = (long long*)bb.take((size_t)h->film_rows * 8);
+  pl->scale = (float*)bb.take(256);
+  // zeroed at the start of every backward: dfilm, affine-norm sums, amax
+  uint8_t* z0 = (uint8_t*)bb.take(0);
+  pl->dfilm = (float*)bb.take((size_t)B * h->film_rows * 4);
+  pl->nsum = (float*)bb.take((size_t)2 * B * kMaxCin * 4);
+  pl->amax = (unsigned int*)bb.take(256);
+  pl->zero_begin = z0; pl->zero_bytes = base ? (size_t)((uint8_t*)pl->amax + 256 - z0) : 0;
+  if (total) *total = stats_bytes + bb.off + 512;
+  if (!base) return 0;
+  pl->bytes = stats_bytes + bb.off;
+  BwdBuilder bw{h, pl, &bb};
+  if (bw.build()) return 1;
+  // flat-gradient offsets of every FiLM row (weights) / element (biases)
+  pl->film_woff_h.assign(h->film_rows, 0); pl->film_boff_h.assign(h->film_rows, 0);
+  auto fill_film = [&](const FilmW& f) {
+    for (int r = 0; r < 2 * f.C; ++r) { pl->film_woff_h[f.off + r] = h->goff[f.w_idx] + (long long)r * CC; pl->film_boff_h[f.off + r] = h->goff[f.b_idx] + r; }
+  };
+  auto fill_rb = [&](const ResBlockW& r) { fill_film(r.n1); fill_film(r.n2); };
+  for (auto& lv : h->d_blocks) for (auto& r : lv) fill_rb(r);
+  for (auto& lv : h->u_blocks) for (auto& r : lv) fill_rb(r);
+  for (auto& r : h->mid) fill_rb(r);
+  return 0;
+}
+
+// cond_k >= 0: the conditioning of this evaluation was computed up front by sampler_conditioning (FiLM rows at film_all + k)
 int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigma, int sigma_is_scalar, const float* obs,
-                const int64_t* act, cudaStream_t st, int prescaled = 0) {
+                const int64_t* act, cudaStream_t st, int prescaled = 0, StackView sv = StackView{}, int cond_k = -1) {
   const dmd_denoiser_config& c = h->cfg;
   const int HW = pl.H * pl.W;
   DMD_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st));
   pack_denoiser_input_kernel<<<dim3((HW + 255) / 256, pl.B), 256, 0, st>>>(
       noisy, obs, sigma, sigma_is_scalar, pl.xin, pl.cs, c.num_steps_conditioning * c.img_channels, c.img_channels,
-      pl.CP_in, HW, c.sigma_data, c.sigma_offset_noise, prescaled);
+      pl.CP_in, HW, c.sigma_data, c.sigma_offset_noise, prescaled, sv);
   DMD_LAUNCH_OK();
-  {
+  const float* film = pl.film;
+  if (cond_k >= 0) {
+    film = pl.film_all + (size_t)cond_k * pl.B * h->film_rows;
+  } else {
     const int total = pl.B * c.cond_channels;
-    cond_embed_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.cs, act, h->ptrs[h->i_fourier], h->ptrs[h->i_actemb], pl.cemb,
-                                                           pl.B, c.cond_channels, c.num_steps_conditioning, c.num_actions);
+    cond_embed_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.cs, nullptr, c.sigma_data, c.sigma_offset_noise, act, h->ptrs[h->i_fourier],
+                                                           h->ptrs[h->i_actemb], pl.cemb, pl.B, pl.B, c.cond_channels, c.num_steps_conditioning,
+                                                           c.num_actions, sv);
     DMD_LAUNCH_OK();
+    if (linear_launch(pl.cemb, h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b], pl.chid, pl.B, c.cond_channels, c.cond_channels, 1, st)) return 1;
+    if (linear_launch(pl.chid, h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, pl.B, c.cond_channels, c.cond_channels, 0, st)) return 1;
+    if (linear_launch(pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film,
+                      pl.B, c.cond_channels, h->film_rows, 0, st)) return 1;
   }
-  if (linear_launch(pl.cemb, h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b], pl.chid, pl.B, c.cond_channels, c.cond_channels, 1, st)) return 1;
-  if (linear_launch(pl.chid, h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond, pl.B, c.cond_channels, c.cond_channels, 0, st)) return 1;
-  if (linear_launch(pl.cond, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film,
-                    pl.B, c.cond_channels, h->film_rows, 0, st)) return 1;
   for (const Op& op : pl.ops) {
     if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
-    else if (op.kind == OP_PREP) { if (prep_launch(op.prep, op.prep_nsrc, st)) return 1; }
+    else if (op.kind == OP_PREP) {
+      if (op.prep.film != nullptr && op.prep.film != film) { PrepParams pp = op.prep; pp.film = film; if (prep_launch(pp, op.prep_nsrc, st)) return 1; }
+      else if (prep_launch(op.prep, op.prep_nsrc, st)) return 1;
+    }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
   return 0;
@@ -690,12 +1141,14 @@ int ensure_plan(dmd_denoiser* h, int B, int H, int W, void* ws, size_t ws_bytes)
   DMD_CHECK(!h->ptrs.empty() && h->packed, "denoiser: call dmd_denoiser_set_weights first");
   Plan& pl = h->plan;
   if (pl.B == B && pl.H == H && pl.W == W && pl.base == (uint8_t*)ws) return 0;
+  // size and validate on a scratch plan: the cached plan is replaced only after every check has passed, and is
+  // invalidated (never left half-written) if the real build fails
   size_t need = 0;
-  if (make_plan(h, &pl, B, H, W, nullptr, &need)) return 1;
+  { Plan tmp; if (make_plan(h, &tmp, B, H, W, nullptr, &need)) return 1; }
   DMD_CHECK(ws && ws_bytes >= need, "denoiser: workspace too small (%zu < %zu)", ws_bytes, need);
   DMD_CHECK(((uintptr_t)ws & 255) == 0, "denoiser: workspace must be 256-byte aligned");
-  if (make_plan(h, &pl, B, H, W, (uint8_t*)ws, nullptr)) { pl.B = 0; return 1; }
-  h->graph.valid = false;
+  for (auto& g : h->graphs) g.valid = false;
+  if (make_plan(h, &pl, B, H, W, (uint8_t*)ws, nullptr)) { pl.B = 0; pl.base = nullptr; pl.ops.clear(); return 1; }
   return 0;
 }
 
@@ -714,15 +1167,18 @@ extern "C" dmd_denoiser* dmd_denoiser_create(const dmd_denoiser_config* cfg) {
 }
 extern "C" void dmd_denoiser_destroy(dmd_denoiser* h) {
   if (!h) return;
-  if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
-  if (h->graph.cap_stream) cudaStreamDestroy(h->graph.cap_stream);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_tensors; }
 extern "C" size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h) { return h->packed_bytes; }
 
 static int pack_one(dmd_denoiser* h, const ConvW& c, cudaStream_t st) {
-  return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.precise, st);
+  if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.precise, st)) return 1;
+  for (int k = 0; k < c.nsrcT; ++k)  // backward-data packs (transposed, flipped), one per concat source
+    if (dmd_pack_conv_weight_dgrad(h->ptrs[c.w_idx], h->packed + c.pkT_off[k], c.Cout, c.CinReal, c.srcOff[k], c.srcC[k], c.taps, st)) return 1;
+  return 0;
 }
 static int pack_rb(dmd_denoiser* h, const ResBlockW& r, cudaStream_t st) {
   const int CC = h->cfg.cond_channels;
@@ -742,7 +1198,7 @@ extern "C" int dmd_denoiser_set_weights(dmd_denoiser* h, const float* const* ptr
   const bool moved = h->packed != (uint8_t*)packed || h->ptrs.empty() || memcmp(h->ptrs.data(), ptrs_host, sizeof(float*) * n_ptrs) != 0;
   h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
   h->packed = (uint8_t*)packed;
-  if (moved) { h->plan.B = 0; h->graph.valid = false; }
+  if (moved) { h->plan.B = 0; h->tplans.clear(); for (auto& g : h->graphs) g.valid = false; }
   if (pack_one(h, h->conv_in, st) || pack_one(h, h->conv_out, st)) return 1;
   for (auto& lv : h->d_blocks) for (auto& r : lv) if (pack_rb(h, r, st)) return 1;
   for (auto& lv : h->u_blocks) for (auto& r : lv) if (pack_rb(h, r, st)) return 1;
@@ -778,124 +1234,290 @@ extern "C" int dmd_inner_model_forward(dmd_denoiser* h, int B, int H, int W, con
   return run_wrap(h, h->plan, noisy_rescaled, out, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1.f, 0.f, st);
 }
 
-// ---------------------------------------------------------------------------------------------- sampler
+// ---------------------------------------------------------------------------------------------- training entry points
 namespace {
 
-__global__ void fill_scalar_kernel(float* p, float v) { *p = v; }
+Plan* find_train_plan(dmd_denoiser* h, int B, int H, int W, void* ws) {
+  for (auto& p : h->tplans)
+    if (p->B == B && p->H == H && p->W == W && p->base == (uint8_t*)ws) return p.get();
+  return nullptr;
+}
 
-int sampler_body(dmd_denoiser* h, const dmd_sampler_config* sc, bool has_eps, cudaStream_t st) {
-  Plan& pl = h->plan;
-  const int n = sc->num_sigmas;
-  const size_t img_elems = (size_t)pl.B * h->cfg.img_channels * pl.H * pl.W;
-  const int total = (int)img_elems;
-  // diffusion_sampler.py:35  gamma_ = min(s_churn / (len(sigmas) - 1), 2**0.5 - 1)
-  const double gamma_ = std::fmin((double)sc->s_churn / (double)(n - 1), std::sqrt(2.0) - 1.0);
-  float* sig_dev = pl.cs + (size_t)pl.B * 4;  // one spare float4 slot after cs (see make_plan: +256 B slack)
-  int cur = 0;
-  for (int i = 0; i + 1 < n; ++i) {
-    const float sigma = sc->sigmas_host[i], next_sigma = sc->sigmas_host[i + 1];
-    const double gamma = (sc->s_tmin <= sigma && sigma <= sc->s_tmax) ? gamma_ : 0.0;
-    const float sigma_hat = sigma * (float)(gamma + 1.0);
-    float* x = pl.s_x[cur];
-    if (gamma > 0.0) {
-      DMD_CHECK(has_eps, "sampler: s_churn > 0 needs eps noise from the caller");
-      const float cfac = std::sqrt(sigma_hat * sigma_hat - sigma * sigma);
-      // x = x + (eps * s_noise) * c   (two roundings as in the reference); s_noise folded when it is exactly 1
-      DMD_CHECK(sc->s_noise == 1.0f, "sampler: s_noise != 1 not built yet");
-      axpy_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, pl.s_eps + (size_t)i * img_elems, cfac, x, total);
-      DMD_LAUNCH_OK();
+int ensure_train_plan(dmd_denoiser* h, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t st, Plan** out) {
+  DMD_CHECK(!h->ptrs.empty() && h->packed, "denoiser: call dmd_denoiser_set_weights first");
+  if ((*out = find_train_plan(h, B, H, W, ws)) != nullptr) return 0;
+  size_t need = 0;
+  { Plan tmp; if (make_train_plan(h, &tmp, B, H, W, nullptr, &need)) return 1; }
+  DMD_CHECK(ws && ws_bytes >= need, "denoiser: training workspace too small (%zu < %zu)", ws_bytes, need);
+  DMD_CHECK(((uintptr_t)ws & 255) == 0, "denoiser: workspace must be 256-byte aligned");
+  // a plan bound to the same workspace with another shape is stale; keep at most 8 plans
+  for (size_t i = 0; i < h->tplans.size();)
+    if (h->tplans[i]->base == (uint8_t*)ws) h->tplans.erase(h->tplans.begin() + i); else ++i;
+  if (h->tplans.size() >= 8) h->tplans.erase(h->tplans.begin());
+  std::unique_ptr<Plan> pl(new Plan());
+  if (make_train_plan(h, pl.get(), B, H, W, (uint8_t*)ws, nullptr)) return 1;
+  DMD_CUDA(cudaMemcpyAsync(pl->film_woff, pl->film_woff_h.data(), pl->film_woff_h.size() * 8, cudaMemcpyHostToDevice, st));
+  DMD_CUDA(cudaMemcpyAsync(pl->film_boff, pl->film_boff_h.data(), pl->film_boff_h.size() * 8, cudaMemcpyHostToDevice, st));
+  *out = pl.get();
+  h->tplans.push_back(std::move(pl));
+  return 0;
+}
+
+int run_backward(dmd_denoiser* h, Plan& pl, const float* grad_out, float* grads, cudaStream_t st) {
+  const dmd_denoiser_config& c = h->cfg;
+  const int B = pl.B, HW = pl.H * pl.W, CC = c.cond_channels;
+  const float* inv = pl.scale + 1;
+  DMD_CUDA(cudaMemsetAsync(grads, 0, (size_t)h->grad_total * 4, st));
+  DMD_CUDA(cudaMemsetAsync(pl.zero_begin, 0, pl.zero_bytes, st));
+  // loss scale from the incoming gradient, then the scaled NHWC gradient of the model output
+  const long long n_out = (long long)B * c.img_channels * HW;
+  absmax_kernel<<<(int)std::min<long long>((n_out + 255) / 256, 1184), 256, 0, st>>>(grad_out, pl.amax, n_out);
+  DMD_LAUNCH_OK();
+  loss_scale_kernel<<<1, 1, 0, st>>>(pl.amax, pl.scale);
+  DMD_LAUNCH_OK();
+  nchw_to_nhwc_scaled_kernel<<<dim3((HW + 255) / 256, B), 256, 0, st>>>(grad_out, pl.gF, pl.scale, c.img_channels, 8, HW);
+  DMD_LAUNCH_OK();
+  for (const BOp& b : pl.bops) {
+    switch (b.kind) {
+      case B_PREP: if (prep_launch(b.prep, b.prep_nsrc, st)) return 1; break;
+      case B_CONV: if (conv_launch(b.conv, b.smem, b.cols, st)) return 1; break;
+      case B_WGRAD: if (wgrad_launch(b.wg, grads + b.goff, st)) return 1; break;
+      case B_COLSUM: {
+        const int L4 = (b.C < 256 ? b.C : 256) >> 2, lanes = 256 / L4;
+        long long blocks = (b.rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+        if (blocks > 592) blocks = 592;
+        if (blocks < 1) blocks = 1;
+        colsum_kernel<<<dim3((unsigned)blocks, (b.C + 255) / 256), 256, 0, st>>>(b.src, grads + b.goff, b.goff2 >= 0 ? grads + b.goff2 : nullptr, inv, b.rows, b.C, b.Creal);
+        DMD_LAUNCH_OK();
+        break;
+      }
+      case B_NORM1: norm_bwd_pass1_kernel<<<dim3(b.chunks, B), kNormThreads, 0, st>>>(b.nb, b.ppb); DMD_LAUNCH_OK(); break;
+      case B_NORM2: norm_bwd_pass2_kernel<<<dim3(b.chunks, B), kNormThreads, 0, st>>>(b.nb, b.ppb); DMD_LAUNCH_OK(); break;
+      case B_AFFINE:
+        affine_param_grad_kernel<<<(b.nb.C + 127) / 128, 128, 0, st>>>(b.nb.sumA, b.nb.sumB, B, b.nb.C, b.nb.sum_stride, grads + b.goff, grads + b.goff2, inv);
+        DMD_LAUNCH_OK();
+        break;
+      case B_POOL: sumpool2_kernel<<<(unsigned)((b.total4 + 255) / 256), 256, 0, st>>>(b.src, b.dst, b.H, b.W, b.C, b.acc, b.total4); DMD_LAUNCH_OK(); break;
+      case B_ADD: add_kernel<<<(unsigned)((b.total4 + 255) / 256), 256, 0, st>>>(b.src, b.dst, b.acc, b.total4); DMD_LAUNCH_OK(); break;
+      case B_ATTN: {
+        AttnBwdParams ab = b.ab;
+        ab.dgamma = grads + b.goffs[0]; ab.dbeta = grads + b.goffs[1]; ab.dwqkv = grads + b.goffs[2]; ab.dbqkv = grads + b.goffs[3];
+        ab.dwout = grads + b.goffs[4]; ab.dbout = grads + b.goffs[5];
+        DMD_CHECK((ab.C == 64 || ab.C == 32) && ab.L == kAttnL, "attention backward: unsupported shape L=%d C=%d", ab.L, ab.C);
+        const size_t smem = sizeof(float) * ((size_t)ab.L * (ab.C + 1) * 4 + (size_t)ab.L * (3 * ab.C + 4) * 2 + (size_t)(ab.C / 8) * ab.L * 3);
+        if (ab.C == 64) attn_bwd_kernel<64><<<B, kAttnThreads, smem, st>>>(ab);
+        else attn_bwd_kernel<32><<<B, kAttnThreads, smem, st>>>(ab);
+        DMD_LAUNCH_OK();
+        break;
+      }
+      case B_MEMSET: DMD_CUDA(cudaMemsetAsync(b.ms_ptr, 0, b.ms_bytes, st)); break;
+      case B_SGEMM: {
+        float* C = b.c_goff >= 0 ? grads + b.c_goff : b.gc;
+        sgemm_kernel<<<dim3((b.N + 63) / 64, (b.M + 63) / 64), 256, 0, st>>>(b.ga, b.sam, b.sak, b.gb, b.sbk, b.sbn, C, b.ldc, b.M, b.N, b.K, b.use_inv ? inv : nullptr, b.acc);
+        DMD_LAUNCH_OK();
+        break;
+      }
+      case B_FILMW:
+        film_wgrad_kernel<<<(h->film_rows + 7) / 8, 256, 0, st>>>(pl.dfilm, pl.cond, grads, pl.film_woff, pl.film_boff, B, h->film_rows, CC, inv);
+        DMD_LAUNCH_OK();
+        break;
+      case B_LINEAR: if (linear_launch(b.lin_in, b.lin_w, b.lin_b, b.lin_out, B, b.lin_K, b.lin_F, 0, st)) return 1; break;
+      case B_DSILU: dsilu_mul_kernel<<<(unsigned)((b.rows + 255) / 256), 256, 0, st>>>(b.src, b.ga, b.dst, b.rows); DMD_LAUNCH_OK(); break;
+      case B_EMB:
+        embedding_bwd_kernel<<<(B * CC + 255) / 256, 256, 0, st>>>(b.src, pl.t_act, grads + b.goff, B, CC, c.num_steps_conditioning, c.num_actions, inv);
+        DMD_LAUNCH_OK();
+        break;
+      default: return fail("backward: unknown op kind %d", b.kind);
     }
-    fill_scalar_kernel<<<1, 1, 0, st>>>(sig_dev, sigma);
-    DMD_LAUNCH_OK();
-    if (run_forward(h, pl, x, sig_dev, 1, pl.s_obs, pl.s_act, st)) return 1;
-    const float dt = next_sigma - sigma_hat;
-    float* xn = pl.s_x[cur ^ 1];
-    if (sc->order == 1 || next_sigma == 0.0f) {
-      if (run_wrap(h, pl, x, nullptr, nullptr, xn, nullptr, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
-    } else {
-      // Heun: x_2 = x + d*dt ; denoise(x_2, next_sigma) ; x = x + ((d + d_2)/2)*dt
-      if (run_wrap(h, pl, x, nullptr, nullptr, pl.s_x2, pl.s_d, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
-      fill_scalar_kernel<<<1, 1, 0, st>>>(sig_dev, next_sigma);
-      DMD_LAUNCH_OK();
-      if (run_forward(h, pl, pl.s_x2, sig_dev, 1, pl.s_obs, pl.s_act, st)) return 1;
-      if (run_wrap(h, pl, pl.s_x2, nullptr, nullptr, xn, nullptr, pl.s_d, x, 2, next_sigma, dt, st)) return 1;
-    }
-    cur ^= 1;
-    if (pl.s_traj) DMD_CUDA(cudaMemcpyAsync(pl.s_traj + (size_t)(i + 1) * img_elems, pl.s_x[cur], img_elems * 4, cudaMemcpyDeviceToDevice, st));
   }
-  if (cur != 0) DMD_CUDA(cudaMemcpyAsync(pl.s_x[0], pl.s_x[1], img_elems * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 }  // namespace
 
-extern "C" int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int H, int W,
-                                  const float* prev_obs, const int64_t* prev_act, const float* x0, const float* eps,
-                                  float* out_x, float* out_traj, void* workspace, size_t workspace_bytes, int use_graph,
-                                  void* stream) {
-  DMD_CHECK(h && sc && prev_obs && prev_act && x0 && out_x, "sampler: null argument");
+extern "C" size_t dmd_denoiser_train_workspace_bytes(const dmd_denoiser* h, int B, int H, int W) {
+  Plan tmp; size_t need = 0;
+  if (make_train_plan(const_cast<dmd_denoiser*>(h), &tmp, B, H, W, nullptr, &need)) return 0;
+  return need;
+}
+extern "C" long long dmd_denoiser_grad_layout(const dmd_denoiser* h, long long* offsets, long long* numels, int n) {
+  if (!h || n != h->n_tensors) { fail("grad_layout: expected %d entries", h ? h->n_tensors : 0); return -1; }
+  for (int i = 0; i < n; ++i) { if (offsets) offsets[i] = h->goff[i]; if (numels) numels[i] = h->numel[i]; }
+  return h->grad_total;
+}
+
+extern "C" int dmd_inner_model_forward_train(dmd_denoiser* h, int B, int H, int W, const float* noisy_rescaled, const float* c_noise,
+                                             int c_noise_is_scalar, const float* obs_rescaled, const int64_t* act, float* out,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+  DMD_CHECK(h && noisy_rescaled && c_noise && obs_rescaled && act && out, "inner_model_forward_train: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* pl = nullptr;
+  if (ensure_train_plan(h, B, H, W, workspace, workspace_bytes, st, &pl)) return 1;
+  pl->t_act = act;
+  if (run_forward(h, *pl, noisy_rescaled, c_noise, c_noise_is_scalar, obs_rescaled, act, st, 1)) return 1;
+  return run_wrap(h, *pl, noisy_rescaled, out, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1.f, 0.f, st);
+}
+
+extern "C" int dmd_denoiser_backward(dmd_denoiser* h, int B, int H, int W, const float* grad_out, float* grads, long long grads_numel,
+                                     void* workspace, void* stream) {
+  DMD_CHECK(h && grad_out && grads && workspace, "denoiser_backward: null argument");
+  Plan* plp = find_train_plan(h, B, H, W, workspace);
+  DMD_CHECK(plp && plp->train, "denoiser_backward: no matching dmd_inner_model_forward_train on this workspace (B=%d H=%d W=%d)", B, H, W);
+  Plan& pl = *plp;
+  DMD_CHECK(grads_numel >= h->grad_total, "denoiser_backward: gradient buffer too small (%lld < %lld floats)", grads_numel, h->grad_total);
+  DMD_CHECK(((uintptr_t)grads & 15) == 0, "denoiser_backward: gradient buffer must be 16-byte aligned");
+  return run_backward(h, pl, grad_out, grads, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- sampler
+namespace {
+
+__global__ void fill_scalar_kernel(float* p, float v) { *p = v; }
+struct SigmaList { float v[kMaxSamplerEvals]; };
+__global__ void write_sigmas_kernel(float* dst, SigmaList s, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x]; }
+
+struct SamplerIO { const float* obs; const int64_t* act; StackView sv; float* traj; const float* eps; float* out; };
+
+// DiffusionSampler.sample (diffusion_sampler.py:31-58).  traj[0] holds x ~ N(0, 1) on entry; traj[i+1] receives the iterate after
+// step i (the reference's `trajectory` list); the last iterate additionally goes to io.out when that is not the last
+// trajectory slot (e.g. straight into the WorldModelEnv's frame ring).  No staging copies: every buffer is used in place.
+int sampler_body(dmd_denoiser* h, const dmd_sampler_config* sc, const SamplerIO& io, cudaStream_t st) {
+  Plan& pl = h->plan;
+  const dmd_denoiser_config& c = h->cfg;
+  const int n = sc->num_sigmas;
+  const size_t img_elems = (size_t)pl.B * c.img_channels * pl.H * pl.W;
+  const int total = (int)img_elems;
+  // diffusion_sampler.py:35  gamma_ = min(s_churn / (len(sigmas) - 1), 2**0.5 - 1)
+  const double gamma_ = std::fmin((double)sc->s_churn / (double)(n - 1), std::sqrt(2.0) - 1.0);
+  // ---- the sigma of every U-Net evaluation is host-known: conditioning (Fourier + action embedding -> cond MLP -> all 44 FiLM
+  //      linears) of ALL evaluations in four launches up front instead of four per evaluation inside the loop
+  SigmaList sl; int K = 0; bool hoist = true;
+  for (int i = 0; i + 1 < n && hoist; ++i) {
+    const float sigma = sc->sigmas_host[i], next_sigma = sc->sigmas_host[i + 1];
+    const double gamma = (sc->s_tmin <= sigma && sigma <= sc->s_tmax) ? gamma_ : 0.0;
+    if (K + 2 > kMaxSamplerEvals) { hoist = false; break; }
+    sl.v[K++] = sigma * (float)(gamma + 1.0);
+    if (!(sc->order == 1 || next_sigma == 0.0f)) sl.v[K++] = next_sigma;
+  }
+  float* sig_dev = pl.cs + (size_t)pl.B * 4;  // spare slot after cs: the un-hoisted fallback's scalar sigma
+  if (hoist) {
+    write_sigmas_kernel<<<1, 32, 0, st>>>(pl.sig_all, sl, K);
+    DMD_LAUNCH_OK();
+    const int rows = K * pl.B, CC = c.cond_channels;
+    cond_embed_kernel<<<(rows * CC + 255) / 256, 256, 0, st>>>(nullptr, pl.sig_all, c.sigma_data, c.sigma_offset_noise, io.act, h->ptrs[h->i_fourier],
+                                                               h->ptrs[h->i_actemb], pl.cemb_all, rows, pl.B, CC, c.num_steps_conditioning, c.num_actions, io.sv);
+    DMD_LAUNCH_OK();
+    if (linear_launch(pl.cemb_all, h->ptrs[h->i_cp0w], h->ptrs[h->i_cp0b], pl.chid_all, rows, CC, CC, 1, st)) return 1;
+    if (linear_launch(pl.chid_all, h->ptrs[h->i_cp2w], h->ptrs[h->i_cp2b], pl.cond_all, rows, CC, CC, 0, st)) return 1;
+    if (linear_launch(pl.cond_all, (const float*)(h->packed + h->film_w_off), (const float*)(h->packed + h->film_b_off), pl.film_all,
+                      rows, CC, h->film_rows, 0, st)) return 1;
+  }
+  int k = 0;
+  auto forward = [&](const float* x, float sigma_value) -> int {
+    if (hoist) { const int kk = k++; return run_forward(h, pl, x, pl.sig_all + kk, 1, io.obs, io.act, st, 0, io.sv, kk); }
+    fill_scalar_kernel<<<1, 1, 0, st>>>(sig_dev, sigma_value);
+    DMD_LAUNCH_OK();
+    return run_forward(h, pl, x, sig_dev, 1, io.obs, io.act, st, 0, io.sv, -1);
+  };
+  for (int i = 0; i + 1 < n; ++i) {
+    const float sigma = sc->sigmas_host[i], next_sigma = sc->sigmas_host[i + 1];
+    const double gamma = (sc->s_tmin <= sigma && sigma <= sc->s_tmax) ? gamma_ : 0.0;
+    const float sigma_hat = sigma * (float)(gamma + 1.0);
+    const float* x = io.traj + (size_t)i * img_elems;
+    float* xn = io.traj + (size_t)(i + 1) * img_elems;
+    if (gamma > 0.0) {  // churn: x + eps * sqrt(sigma_hat^2 - sigma^2) (diffusion_sampler.py:41-43); the trajectory keeps the un-churned x
+      DMD_CHECK(io.eps != nullptr, "sampler: s_churn > 0 needs eps noise from the caller");
+      DMD_CHECK(sc->s_noise == 1.0f, "sampler: s_noise != 1 not built yet");
+      const float cfac = std::sqrt(sigma_hat * sigma_hat - sigma * sigma);
+      axpy_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, io.eps + (size_t)i * img_elems, cfac, pl.s_xc, total);
+      DMD_LAUNCH_OK();
+      x = pl.s_xc;
+    }
+    if (forward(x, sigma_hat)) return 1;
+    const float dt = next_sigma - sigma_hat;
+    if (sc->order == 1 || next_sigma == 0.0f) {
+      if (run_wrap(h, pl, x, nullptr, nullptr, xn, nullptr, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
+    } else {
+      // Heun: x_2 = x + d*dt ; denoise(x_2, next_sigma) ; x = x + ((d + d_2)/2)*dt
+      if (run_wrap(h, pl, x, nullptr, nullptr, pl.s_x2, pl.s_d, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
+      if (forward(pl.s_x2, next_sigma)) return 1;
+      if (run_wrap(h, pl, pl.s_x2, nullptr, nullptr, xn, nullptr, pl.s_d, x, 2, next_sigma, dt, st)) return 1;
+    }
+  }
+  float* last = io.traj + (size_t)(n - 1) * img_elems;
+  if (io.out && io.out != last) DMD_CUDA(cudaMemcpyAsync(io.out, last, img_elems * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int H, int W, const float* prev_obs,
+                                  const int64_t* prev_act, int ring_head, float* traj, const float* eps, float* out_x,
+                                  void* workspace, size_t workspace_bytes, int use_graph, void* stream) {
+  DMD_CHECK(h && sc && prev_obs && prev_act && traj, "sampler: null argument");
   DMD_CHECK(sc->num_sigmas >= 2 && sc->sigmas_host, "sampler: need at least 2 sigmas");
   DMD_CHECK(sc->order == 1 || sc->order == 2, "sampler: order must be 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
   const dmd_denoiser_config& c = h->cfg;
-  const size_t img_elems = (size_t)B * c.img_channels * H * W;
-  const int n = sc->num_sigmas;
+  const int n = sc->num_sigmas, T = c.num_steps_conditioning;
+  DMD_CHECK(ring_head >= -1 && ring_head < T, "sampler: ring_head must be -1 (contiguous stacks) or a slot index < %d", T);
   if (init_kernels()) return 1;
-  // the trajectory / eps staging buffers live at the tail of the workspace
   if (h->need_B != B || h->need_H != H || h->need_W != W) {
     h->need_bytes = dmd_denoiser_workspace_bytes(h, B, H, W);
     h->need_B = B; h->need_H = H; h->need_W = W;
   }
-  const size_t core = h->need_bytes;
-  DMD_CHECK(core > 0, "sampler: %s", g_err.c_str());
-  const size_t traj_bytes = img_elems * 4 * n, eps_bytes = eps ? img_elems * 4 * (n - 1) : 0;
-  DMD_CHECK(workspace_bytes >= core + traj_bytes + eps_bytes + 512, "sampler: workspace too small (%zu < %zu)", workspace_bytes, core + traj_bytes + eps_bytes + 512);
-  if (ensure_plan(h, B, H, W, workspace, core)) return 1;
-  Plan& pl = h->plan;
-  uint8_t* tail = (uint8_t*)workspace + ((core + 255) & ~(size_t)255);
-  pl.s_traj = (float*)tail;
-  pl.s_eps = eps ? (float*)(tail + ((traj_bytes + 255) & ~(size_t)255)) : nullptr;
-
-  DMD_CUDA(cudaMemcpyAsync(pl.s_obs, prev_obs, img_elems * 4 * c.num_steps_conditioning, cudaMemcpyDeviceToDevice, st));
-  DMD_CUDA(cudaMemcpyAsync(pl.s_act, prev_act, (size_t)B * c.num_steps_conditioning * 8, cudaMemcpyDeviceToDevice, st));
-  DMD_CUDA(cudaMemcpyAsync(pl.s_x[0], x0, img_elems * 4, cudaMemcpyDeviceToDevice, st));
-  DMD_CUDA(cudaMemcpyAsync(pl.s_traj, x0, img_elems * 4, cudaMemcpyDeviceToDevice, st));
-  if (eps) DMD_CUDA(cudaMemcpyAsync(pl.s_eps, eps, eps_bytes, cudaMemcpyDeviceToDevice, st));
-
+  DMD_CHECK(h->need_bytes > 0, "sampler: %s", g_err.c_str());
+  DMD_CHECK(workspace_bytes >= h->need_bytes, "sampler: workspace too small (%zu < %zu)", workspace_bytes, h->need_bytes);
+  if (ensure_plan(h, B, H, W, workspace, workspace_bytes)) return 1;
+  SamplerIO io; memset(&io, 0, sizeof(io));
+  io.obs = prev_obs; io.act = prev_act; io.traj = traj; io.eps = eps; io.out = out_x;
+  if (ring_head >= 0) {  // frames (T, B, C, H, W), acts (T, B); logical slot k = physical (ring_head + k) % T
+    const long long chw = (long long)c.img_channels * H * W;
+    io.sv = StackView{T, ring_head, (long long)B * chw, chw, (long long)B, 1};
+  }
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   DMD_CUDA(cudaStreamIsCapturing(st, &cap));
-  if (!use_graph || cap != cudaStreamCaptureStatusNone) {
-    if (sampler_body(h, sc, eps != nullptr, st)) return 1;
-  } else {
-    SamplerGraph& g = h->graph;
-    const float churn[4] = {sc->s_churn, sc->s_tmin, sc->s_tmax, sc->s_noise};
-    bool same = g.valid && g.B == B && g.H == H && g.W == W && g.ws == workspace && g.order == sc->order &&
-                g.has_eps == (eps != nullptr) && (int)g.sigmas.size() == n &&
-                memcmp(g.sigmas.data(), sc->sigmas_host, 4 * n) == 0 && memcmp(g.churn, churn, sizeof(churn)) == 0;
-    if (!same) {
-      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-      g.valid = false;
-      cudaGraph_t graph = nullptr;
-      if (!g.cap_stream) DMD_CUDA(cudaStreamCreateWithFlags(&g.cap_stream, cudaStreamNonBlocking));
-      DMD_CUDA(cudaStreamBeginCapture(g.cap_stream, cudaStreamCaptureModeThreadLocal));
-      const long long before = g_launches;
-      int rc = sampler_body(h, sc, eps != nullptr, g.cap_stream);
-      cudaError_t ce = cudaStreamEndCapture(g.cap_stream, &graph);
-      g.kernels = g_launches - before;
-      g_launches = before;  // capture does not execute
-      if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
-      DMD_CHECK(ce == cudaSuccess, "sampler: graph capture failed: %s", cudaGetErrorString(ce));
-      ce = cudaGraphInstantiate(&g.exec, graph, 0);
-      cudaGraphDestroy(graph);
-      DMD_CHECK(ce == cudaSuccess, "sampler: graph instantiate failed: %s", cudaGetErrorString(ce));
-      g.valid = true; g.B = B; g.H = H; g.W = W; g.ws = workspace; g.order = sc->order; g.has_eps = eps != nullptr;
-      g.sigmas.assign(sc->sigmas_host, sc->sigmas_host + n); memcpy(g.churn, churn, sizeof(churn));
-    }
-    DMD_CUDA(cudaGraphLaunch(g.exec, st));
-    g_launches += g.kernels;
+  if (!use_graph || cap != cudaStreamCaptureStatusNone) return sampler_body(h, sc, io, st);
+
+  const float churn[4] = {sc->s_churn, sc->s_tmin, sc->s_tmax, sc->s_noise};
+  SamplerGraph* g = nullptr;
+  for (auto& cand : h->graphs) {
+    if (cand.valid && cand.B == B && cand.H == H && cand.W == W && cand.ws == workspace && cand.order == sc->order &&
+        cand.obs == prev_obs && cand.act == prev_act && cand.traj == traj && cand.eps == eps && cand.out == out_x &&
+        cand.sv.ring_T == io.sv.ring_T && cand.sv.head == io.sv.head && (int)cand.sigmas.size() == n &&
+        memcmp(cand.sigmas.data(), sc->sigmas_host, 4 * n) == 0 && memcmp(cand.churn, churn, sizeof(churn)) == 0) { g = &cand; break; }
   }
-  DMD_CUDA(cudaMemcpyAsync(out_x, pl.s_x[0], img_elems * 4, cudaMemcpyDeviceToDevice, st));
-  if (out_traj) DMD_CUDA(cudaMemcpyAsync(out_traj, pl.s_traj, traj_bytes, cudaMemcpyDeviceToDevice, st));
+  if (!g) {
+    // graphs bake the buffer addresses in: one graph per distinct set (a WorldModelEnv cycles through T ring heads); keep 8
+    if (h->graphs.size() >= 8) {
+      size_t victim = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[victim].stamp) victim = i;
+      if (h->graphs[victim].exec) cudaGraphExecDestroy(h->graphs[victim].exec);
+      h->graphs.erase(h->graphs.begin() + victim);
+    }
+    SamplerGraph ng;
+    cudaGraph_t graph = nullptr;
+    if (!h->cap_stream) DMD_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    DMD_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = g_launches;
+    int rc = sampler_body(h, sc, io, h->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    ng.kernels = g_launches - before;
+    g_launches = before;  // capture does not execute
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    DMD_CHECK(ce == cudaSuccess, "sampler: graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    DMD_CHECK(ce == cudaSuccess, "sampler: graph instantiate failed: %s", cudaGetErrorString(ce));
+    ng.valid = true; ng.B = B; ng.H = H; ng.W = W; ng.ws = workspace; ng.order = sc->order; ng.has_eps = eps != nullptr;
+    ng.obs = prev_obs; ng.act = prev_act; ng.traj = traj; ng.eps = eps; ng.out = out_x; ng.sv = io.sv;
+    ng.sigmas.assign(sc->sigmas_host, sc->sigmas_host + n); memcpy(ng.churn, churn, sizeof(churn));
+    h->graphs.push_back(ng);
+    g = &h->graphs.back();
+  }
+  g->stamp = ++h->graph_clock;
+  DMD_CUDA(cudaGraphLaunch(g->exec, st));
+  g_launches += g->kernels;
   return 0;
 }
 
@@ -911,15 +1533,22 @@ struct dmd_actor_critic {
   size_t packed_bytes = 0;
   std::vector<const float*> ptrs;
   uint8_t* packed = nullptr;
+  std::vector<long long> numel, goff;   // flat gradient layout (state_dict order), as for the denoiser
+  long long grad_total = 0;
 };
 
 namespace {
 
-ConvW ac_conv(int& idx, size_t& pk, int cout, int cin_real, int taps, int c0_store) {
+ConvW ac_conv(dmd_actor_critic* h, int& idx, size_t& pk, int cout, int cin_real, int taps, int c0_store, bool dgrad) {
   ConvW c; c.w_idx = idx++; c.b_idx = idx++;
+  h->numel.push_back((long long)cout * cin_real * taps); h->numel.push_back(cout);
   c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
   c.c0_real = cin_real; c.c0_store = c0_store; c.Cin = round_up(c0_store, 16);
   c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2; pk = (pk + 255) & ~(size_t)255;
+  if (dgrad) {
+    c.nsrcT = 1; c.srcC[0] = cin_real; c.srcOff[0] = 0; c.pkT_off[0] = pk;
+    pk += (size_t)taps * round_up(cout, 16) * round_up(cin_real, 16) * 2; pk = (pk + 255) & ~(size_t)255;
+  }
   return c;
 }
 
@@ -971,22 +1600,29 @@ extern "C" dmd_actor_critic* dmd_actor_critic_create(const dmd_actor_critic_conf
   int idx = 0; size_t pk = 0;
   // registration order (actor_critic.py:41-47,101-110): encoder.encoder.{0: Conv3x3, k: SmallResBlock(f.0.norm, f.2, skip_projection),
   // MaxPool...}, lstm.{weight_ih, weight_hh, bias_ih, bias_hh}, critic_linear, actor_linear
-  h->conv0 = ac_conv(idx, pk, cfg->channels[0], cfg->img_channels, 9, round_up(cfg->img_channels, 16));
+  h->conv0 = ac_conv(h, idx, pk, cfg->channels[0], cfg->img_channels, 9, round_up(cfg->img_channels, 16), false);
   int S = cfg->img_size;
   for (int i = 0; i < cfg->num_levels; ++i) {
     dmd_actor_critic::Level lv;
     lv.cin = cfg->channels[i > 0 ? i - 1 : 0]; lv.cout = cfg->channels[i]; lv.down = cfg->down[i] ? 1 : 0;
     lv.gn_w = idx++; lv.gn_b = idx++;
-    lv.conv = ac_conv(idx, pk, lv.cout, lv.cin, 9, lv.cin);
+    h->numel.push_back(lv.cin); h->numel.push_back(lv.cin);
+    lv.conv = ac_conv(h, idx, pk, lv.cout, lv.cin, 9, lv.cin, true);
     lv.has_skip = lv.cin != lv.cout;
-    if (lv.has_skip) lv.skip = ac_conv(idx, pk, lv.cout, lv.cin, 1, lv.cin);
+    if (lv.has_skip) lv.skip = ac_conv(h, idx, pk, lv.cout, lv.cin, 1, lv.cin, true);
     h->levels.push_back(lv);
     if (lv.down) S /= 2;
   }
   h->feat_c = cfg->channels[cfg->num_levels - 1]; h->feat_hw = S * S;
   h->i_wih = idx++; h->i_whh = idx++; h->i_bih = idx++; h->i_bhh = idx++;
   h->i_cw = idx++; h->i_cb = idx++; h->i_aw = idx++; h->i_ab = idx++;
+  {
+    const long long D = cfg->lstm_dim, K = (long long)h->feat_c * h->feat_hw;
+    for (long long n : {4 * D * K, 4 * D * D, 4 * D, 4 * D, D, 1ll, (long long)cfg->num_actions * D, (long long)cfg->num_actions}) h->numel.push_back(n);
+  }
   h->n_tensors = idx; h->packed_bytes = pk + 256;
+  h->goff.assign(idx, 0);
+  for (int i = 0; i < idx; ++i) { h->goff[i] = h->grad_total; h->grad_total += (h->numel[i] + 3) & ~3ll; }
   return h;
 }
 extern "C" void dmd_actor_critic_destroy(dmd_actor_critic* h) { delete h; }
@@ -999,7 +1635,10 @@ extern "C" int dmd_actor_critic_set_weights(dmd_actor_critic* h, const float* co
   h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
   h->packed = (uint8_t*)packed;
   auto pack = [&](const ConvW& c) {
-    return dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, 0, stream);
+    if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, 0, stream)) return 1;
+    for (int k = 0; k < c.nsrcT; ++k)
+      if (dmd_pack_conv_weight_dgrad(h->ptrs[c.w_idx], h->packed + c.pkT_off[k], c.Cout, c.CinReal, c.srcOff[k], c.srcC[k], c.taps, stream)) return 1;
+    return 0;
   };
   if (pack(h->conv0)) return 1;
   for (auto& lv : h->levels) { if (pack(lv.conv)) return 1; if (lv.has_skip && pack(lv.skip)) return 1; }
@@ -1067,5 +1706,202 @@ extern "C" int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float*
   DMD_LAUNCH_OK();
   if (linear_launch(hx_out, h->ptrs[h->i_aw], h->ptrs[h->i_ab], logits, B, D, c.num_actions, 0, st)) return 1;
   if (linear_launch(hx_out, h->ptrs[h->i_cw], h->ptrs[h->i_cb], val, B, D, 1, 0, st)) return 1;
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- actor-critic training
+// ActorCritic.predict_act_value under autograd (actor_critic.py:68-73, called with grad from env_loop.py:31,57): the forward
+// above leaves every activation in its workspace; dmd_actor_critic_backward consumes it.  One call = one autograd node of
+// the BPTT graph; torch's engine chains the nodes through (g_hx_in, g_cx_in) and accumulates the parameter gradients.
+namespace {
+
+struct AcScratch {
+  float *g_a, *g_b, *tA; uint8_t *gy_op, *x_op; float *dgates, *g_h, *g_xflat, *x_flat, *nsum, *scale, *partial; unsigned int* amax; size_t total;
+};
+int ac_scratch_layout(const dmd_actor_critic* h, int B, uint8_t* base, AcScratch* o) {
+  const dmd_actor_critic_config& c = h->cfg;
+  Bump bb{base};
+  const int S = c.img_size;
+  const size_t act = (size_t)B * S * S * 64 * 4;
+  o->g_a = (float*)bb.take(act); o->g_b = (float*)bb.take(act); o->tA = (float*)bb.take(act);
+  o->gy_op = (uint8_t*)bb.take(plc16_bytes(B, S, S, 64)); o->x_op = (uint8_t*)bb.take(plc16_bytes(B, S, S, 64));
+  const int D = c.lstm_dim, K = h->feat_c * h->feat_hw;
+  o->dgates = (float*)bb.take((size_t)B * 4 * D * 4); o->g_h = (float*)bb.take((size_t)B * D * 4);
+  o->g_xflat = (float*)bb.take((size_t)B * K * 4); o->x_flat = (float*)bb.take((size_t)B * K * 4);
+  o->nsum = (float*)bb.take((size_t)2 * B * kMaxCin * 4);
+  o->scale = (float*)bb.take(256); o->amax = (unsigned int*)bb.take(256);
+  if (init_kernels()) return 1;
+  o->partial = (float*)bb.take(wgrad_partial_bytes(g_num_sms));
+  o->total = bb.off + 256;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t dmd_actor_critic_backward_scratch_bytes(const dmd_actor_critic* h, int B) {
+  AcScratch s; if (ac_scratch_layout(h, B, nullptr, &s)) return 0; return s.total;
+}
+extern "C" long long dmd_actor_critic_grad_layout(const dmd_actor_critic* h, long long* offsets, long long* numels, int n) {
+  if (!h || n != h->n_tensors) { fail("ac grad_layout: expected %d entries", h ? h->n_tensors : 0); return -1; }
+  for (int i = 0; i < n; ++i) { if (offsets) offsets[i] = h->goff[i]; if (numels) numels[i] = h->numel[i]; }
+  return h->grad_total;
+}
+
+extern "C" int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                                         const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
+                                         float* grads, long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace,
+                                         void* scratch, size_t scratch_bytes, void* stream) {
+  DMD_CHECK(h && hx_in && cx_in && hx_out && grads && g_hx_in && g_cx_in && workspace && scratch, "ac backward: null argument");
+  DMD_CHECK(!h->ptrs.empty() && h->packed, "ac backward: call dmd_actor_critic_set_weights first");
+  DMD_CHECK(grads_numel >= h->grad_total && ((uintptr_t)grads & 15) == 0, "ac backward: bad gradient buffer");
+  DMD_CHECK(((uintptr_t)scratch & 255) == 0, "ac backward: scratch must be 256-byte aligned");
+  const dmd_actor_critic_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  AcBuffers b; ac_layout(h, B, (uint8_t*)workspace, &b);
+  AcScratch sc; if (ac_scratch_layout(h, B, (uint8_t*)scratch, &sc)) return 1;
+  DMD_CHECK(scratch_bytes >= sc.total, "ac backward: scratch too small (%zu < %zu)", scratch_bytes, sc.total);
+  const int D = c.lstm_dim, A = c.num_actions, K = h->feat_c * h->feat_hw;
+  auto G = [&](int idx) { return grads + h->goff[idx]; };
+  auto sgemm = [&](const float* Am, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long ldc,
+                   int M, int N, int Kd, int acc) -> int {
+    sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(Am, sam, sak, Bm, sbk, sbn, C, ldc, M, N, Kd, nullptr, acc);
+    DMD_LAUNCH_OK();
+    return 0;
+  };
+  auto colsum = [&](const float* x, long long rows, int C, int Creal, float* out, float* out2, const float* inv) -> int {
+    const int L4 = (C < 256 ? C : 256) >> 2, lanes = 256 / L4;
+    long long blocks = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+    blocks = blocks > 592 ? 592 : (blocks < 1 ? 1 : blocks);
+    colsum_kernel<<<dim3((unsigned)blocks, (C + 255) / 256), 256, 0, st>>>(x, out, out2, inv, rows, C, Creal);
+    DMD_LAUNCH_OK();
+    return 0;
+  };
+  DMD_CUDA(cudaMemsetAsync(grads, 0, (size_t)h->grad_total * 4, st));
+  DMD_CUDA(cudaMemsetAsync(sc.amax, 0, 256, st));
+  // ---- heads (actor_critic.py:73)
+  heads_bwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(g_hx, g_logits, g_val, h->ptrs[h->i_aw], h->ptrs[h->i_cw], sc.g_h, B, D, A);
+  DMD_LAUNCH_OK();
+  if (g_logits) {
+    if (sgemm(g_logits, 1, A, hx_out, D, 1, G(h->i_aw), D, A, D, B, 1)) return 1;          // dWa += g_logits^T h'
+    small_colsum_kernel<<<(A + 31) / 32, 32, 0, st>>>(g_logits, B, A, G(h->i_ab));           // dba (A need not be a multiple of 4)
+    DMD_LAUNCH_OK();
+  }
+  if (g_val) { vec_outer_sum_kernel<<<(D + 127) / 128, 128, 0, st>>>(g_val, hx_out, G(h->i_cw), G(h->i_cb), B, D); DMD_LAUNCH_OK(); }
+  // ---- LSTMCell (actor_critic.py:72)
+  lstm_cell_bwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(b.gates, cx_in, sc.g_h, g_cx, sc.dgates, g_cx_in, B, D);
+  DMD_LAUNCH_OK();
+  const float* feat = b.pooled[h->levels.size()];
+  if (dmd_nhwc_to_nchw(feat, sc.x_flat, B, h->feat_c, h->feat_c, h->feat_hw, st)) return 1;   // x.flatten(start_dim=1) of the NCHW feature map
+  if (sgemm(sc.dgates, 1, 4 * D, sc.x_flat, K, 1, G(h->i_wih), K, 4 * D, K, B, 1)) return 1;  // dWih += dgates^T x
+  if (sgemm(sc.dgates, 1, 4 * D, hx_in, D, 1, G(h->i_whh), D, 4 * D, D, B, 1)) return 1;      // dWhh += dgates^T hx
+  if (colsum(sc.dgates, B, 4 * D, 4 * D, G(h->i_bih), G(h->i_bhh), nullptr)) return 1;
+  if (sgemm(sc.dgates, 4 * D, 1, h->ptrs[h->i_whh], D, 1, g_hx_in, D, B, D, 4 * D, 0)) return 1;   // g_hx = dgates Whh
+  if (sgemm(sc.dgates, 4 * D, 1, h->ptrs[h->i_wih], K, 1, sc.g_xflat, K, B, K, 4 * D, 0)) return 1;  // g_x = dgates Wih
+  // ---- encoder (actor_critic.py:101-113): the feature gradient enters the fp16 tensor-core path with a loss scale
+  float* g_cur = sc.g_a;    // gradient of pooled[i+1]; g_a / g_b ping-pong down the encoder
+  auto other = [&](float* p) { return p == sc.g_a ? sc.g_b : sc.g_a; };
+  if (dmd_nchw_to_nhwc(sc.g_xflat, g_cur, B, h->feat_c, h->feat_c, h->feat_hw, st)) return 1;
+  {
+    const long long n = (long long)B * K;
+    absmax_kernel<<<(int)std::min<long long>((n + 255) / 256, 592), 256, 0, st>>>(g_cur, sc.amax, n);
+    DMD_LAUNCH_OK();
+    loss_scale_kernel<<<1, 1, 0, st>>>(sc.amax, sc.scale);
+    DMD_LAUNCH_OK();
+    scale_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g_cur, sc.scale, n);
+    DMD_LAUNCH_OK();
+  }
+  const float* inv = sc.scale + 1;
+  auto prep = [&](const float* src, int Csrc, int hw, int mode, int gamma_idx, int beta_idx, const double* stats, uint8_t* dst) -> int {
+    dmd_prep_desc pd; memset(&pd, 0, sizeof(pd));
+    pd.src0 = src; pd.C0 = Csrc; pd.B = B; pd.Hs = hw; pd.Ws = hw; pd.mode = mode; pd.silu = mode ? 1 : 0;
+    pd.stats0 = stats; pd.gs0 = mode ? gn_group_size(Csrc) : 0;
+    if (mode) { pd.gamma = h->ptrs[gamma_idx]; pd.beta = h->ptrs[beta_idx]; }
+    pd.eps = kGnEps; pd.dst0 = dst;
+    PrepParams pp; int nsrc;
+    if (prep_fill(&pd, &pp, &nsrc)) return 1;
+    return prep_launch(pp, nsrc, st);
+  };
+  auto wgrad = [&](const ConvW& cw, const uint8_t* gy, const uint8_t* act, int Ca, int hw) -> int {
+    WgradLaunch L;
+    if (wgrad_fill(gy, round_up(cw.Cout, 16), act, Ca, B, hw, hw, cw.taps, sc.partial, cw.Cout, cw.CinReal, cw.CinReal, 0, inv, 1, 0, &L)) return 1;
+    return wgrad_launch(L, G(cw.w_idx), st);
+  };
+  auto dgrad = [&](const ConvW& cw, const uint8_t* gy, int hw, float* out, bool accumulate) -> int {
+    dmd_conv_desc d; memset(&d, 0, sizeof(d));
+    d.src0 = gy; d.C0 = round_up(cw.Cout, 16); d.B = B; d.H = hw; d.W = hw; d.taps = cw.taps; d.stride = 1;
+    d.wpk = h->packed + cw.pkT_off[0]; d.Cout = cw.srcC[0]; d.CoutPad = round_up(cw.srcC[0], 16);
+    d.out = out; d.residual = accumulate ? out : nullptr;
+    ConvParams p; size_t smem; int cols;
+    if (conv_fill(&d, &p, &smem, &cols)) return 1;
+    return conv_launch(p, smem, cols, st);
+  };
+  // spatial size of every level's input
+  std::vector<int> size_in(h->levels.size() + 1);
+  { int S = c.img_size; for (size_t i = 0; i < h->levels.size(); ++i) { size_in[i] = S; if (h->levels[i].down) S /= 2; } size_in[h->levels.size()] = S; }
+  for (int i = (int)h->levels.size() - 1; i >= 0; --i) {
+    const auto& lv = h->levels[i];
+    const int S = size_in[i];
+    const float* gy = g_cur;            // gradient of the SmallResBlock output y[i] (NHWC, S x S x cout)
+    float* gx = other(g_cur);           // gradient of the block input pooled[i]
+    if (lv.down) {                      // un-pool into the other buffer; the pooled gradient's buffer then takes gx
+      const int total = (S / 2) * (S / 2) * lv.cout;
+      maxpool2_bwd_kernel<<<dim3((total + 255) / 256, B), 256, 0, st>>>(b.y[i], g_cur, other(g_cur), S, S, lv.cout);
+      DMD_LAUNCH_OK();
+      gy = other(g_cur);
+      gx = g_cur;
+    }
+    const long long pix = (long long)B * S * S;
+    // SmallResBlock (blocks.py:116-123): y = skip(x) + conv3x3(silu(GroupNorm(x)))
+    if (prep(gy, lv.cout, S, 0, 0, 0, nullptr, sc.gy_op)) return 1;
+    if (colsum(gy, pix, lv.cout, lv.cout, G(lv.conv.b_idx), lv.has_skip ? G(lv.skip.b_idx) : nullptr, inv)) return 1;
+    if (prep(b.pooled[i], lv.cin, S, 2, lv.gn_w, lv.gn_b, b.st_in[i], sc.x_op)) return 1;
+    if (wgrad(lv.conv, sc.gy_op, sc.x_op, round_up(lv.cin, 16), S)) return 1;
+    if (dgrad(lv.conv, sc.gy_op, S, sc.tA, false)) return 1;
+    {
+      NormBwdParams nb; memset(&nb, 0, sizeof(nb));
+      nb.x = b.pooled[i]; nb.gy = sc.tA; nb.stats = b.st_in[i]; nb.B = B; nb.HW = S * S; nb.C = lv.cin; nb.gs = gn_group_size(lv.cin);
+      nb.mode = 2; nb.act = 1; nb.gamma = h->ptrs[lv.gn_w]; nb.beta = h->ptrs[lv.gn_b]; nb.eps = kGnEps;
+      nb.sumA = sc.nsum; nb.sumB = sc.nsum + (size_t)B * kMaxCin; nb.sum_stride = kMaxCin;
+      nb.gx = gx; nb.addend = lv.has_skip ? nullptr : gy; nb.accumulate = 0;
+      DMD_CUDA(cudaMemsetAsync(sc.nsum, 0, (size_t)2 * B * kMaxCin * 4, st));
+      int ppb = nb.HW;
+      while (ppb > 32 && (long long)B * ((nb.HW + ppb - 1) / ppb) < 2 * 148) ppb >>= 1;
+      const int chunks = (nb.HW + ppb - 1) / ppb;
+      norm_bwd_pass1_kernel<<<dim3(chunks, B), kNormThreads, 0, st>>>(nb, ppb);
+      DMD_LAUNCH_OK();
+      affine_param_grad_kernel<<<(nb.C + 127) / 128, 128, 0, st>>>(nb.sumA, nb.sumB, B, nb.C, nb.sum_stride, G(lv.gn_w), G(lv.gn_b), inv);
+      DMD_LAUNCH_OK();
+      norm_bwd_pass2_kernel<<<dim3(chunks, B), kNormThreads, 0, st>>>(nb, ppb);
+      DMD_LAUNCH_OK();
+    }
+    if (lv.has_skip) {  // 1x1 skip projection on the raw input
+      if (prep(b.pooled[i], lv.cin, S, 0, 0, 0, nullptr, sc.x_op)) return 1;
+      if (wgrad(lv.skip, sc.gy_op, sc.x_op, round_up(lv.cin, 16), S)) return 1;
+      if (dgrad(lv.skip, sc.gy_op, S, gx, true)) return 1;
+    }
+    g_cur = gx;
+  }
+  {  // conv0 (Conv3x3(img_channels -> channels[0])): weight / bias gradients only
+    const int S = c.img_size;
+    if (prep(g_cur, h->conv0.Cout, S, 0, 0, 0, nullptr, sc.gy_op)) return 1;
+    if (colsum(g_cur, (long long)B * S * S, h->conv0.Cout, h->conv0.Cout, G(h->conv0.b_idx), nullptr, inv)) return 1;
+    if (prep(b.x0, h->conv0.c0_store, S, 0, 0, 0, nullptr, sc.x_op)) return 1;
+    WgradLaunch L;
+    if (wgrad_fill(sc.gy_op, round_up(h->conv0.Cout, 16), sc.x_op, h->conv0.c0_store, B, S, S, 9, sc.partial, h->conv0.Cout, h->conv0.CinReal,
+                   h->conv0.CinReal, 0, inv, 1, 0, &L)) return 1;
+    if (wgrad_launch(L, G(h->conv0.w_idx), st)) return 1;
+  }
+  return 0;
+}
+
+
+// compute_lambda_returns (actor_critic.py:116-143) on the device, bit-identical to the torch expression.
+extern "C" int dmd_lambda_returns(const float* rew, const int64_t* end, const int64_t* trunc, const float* val_bootstrap, float* out,
+                                  int B, int T, double gamma, double lambda_, void* stream) {
+  DMD_CHECK(rew && end && trunc && val_bootstrap && out && B > 0 && T > 0, "lambda_returns: bad arguments");
+  lambda_returns_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, (const long long*)end, (const long long*)trunc, val_bootstrap, out, B, T,
+                                                                         (float)gamma, (float)lambda_, (float)(1.0 - lambda_));
+  DMD_LAUNCH_OK();
   return 0;
 }

@@ -21,13 +21,19 @@ __device__ __forceinline__ float4 edm_conditioners(float sigma, float sigma_data
   return c;
 }
 
+// Where the frame stack / action stack of the sampler lives.  Default (ring_T = 0): obs (B, T*C, H, W), act (B, T) as the
+// reference passes them.  Ring (ring_T = T): the WorldModelEnv's resident buffers frames (T, B, C, H, W) / acts (T, B), where
+// LOGICAL slot k (0 = oldest) is physical slot (head + k) % T -- the reference's per-step `roll` of both buffers
+// (world_model_env.py:74-75) becomes head = (head + 1) % T and no data moves.
+struct StackView { int ring_T; int head; long long frame_stride; long long batch_stride; long long act_slot_stride; long long act_batch_stride; };
+
 // Pack the conv_in input (inner_model.py:46 cat((obs, noisy)) after denoiser.py:75-76 rescaling) as NHWC with the
 // channel count rounded up to CP (multiple of 8; zero filled).   obs: (B, Cobs, H, W)  noisy: (B, Cimg, H, W) NCHW.
 // Also writes cs[n] (4 floats).  grid: (ceil(H*W/256), B)
 __global__ void pack_denoiser_input_kernel(const float* __restrict__ noisy, const float* __restrict__ obs,
                                            const float* __restrict__ sigma, int sigma_is_scalar, float* __restrict__ xin,
                                            float* __restrict__ cs, int Cobs, int Cimg, int CP, int HW, float sigma_data,
-                                           float sigma_offset, int prescaled) {
+                                           float sigma_offset, int prescaled, StackView sv) {
   const int n = blockIdx.y;
   const float sg = sigma[sigma_is_scalar ? 0 : n];
   // prescaled: caller already applied denoiser.py:75-76 and `sigma` holds c_noise (InnerModel.forward surface)
@@ -39,7 +45,13 @@ __global__ void pack_denoiser_input_kernel(const float* __restrict__ noisy, cons
   for (int ch = 0; ch < CP; ++ch) {
     float v = 0.f;
     if (ch < Cobs) {
-      v = obs[((size_t)n * Cobs + ch) * HW + pix];
+      if (sv.ring_T > 0) {
+        const int f = ch / Cimg, cc = ch - f * Cimg;
+        int pf = sv.head + f; if (pf >= sv.ring_T) pf -= sv.ring_T;
+        v = obs[(size_t)pf * sv.frame_stride + (size_t)n * sv.batch_stride + (size_t)cc * HW + pix];
+      } else {
+        v = obs[((size_t)n * Cobs + ch) * HW + pix];
+      }
       if (!prescaled) v = __fdiv_rn(v, sigma_data);
     } else if (ch < Cobs + Cimg) {
       v = __fmul_rn(noisy[((size_t)n * Cimg + (ch - Cobs)) * HW + pix], c.x);
@@ -68,18 +80,28 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
 // Conditioning path (inner_model.py:45, :27-35; blocks.py:84-87, :39,44), as one embedding kernel + three calls of a
 // small GEMM:   e = fourier(c_noise) + flatten(act_emb(act)) ;  h = silu(W0 e + b0) ;  cond = W1 h + b1 ;
 //               film = Wf cond + bf   (ALL AdaGroupNorm linears of the network batched: Wf = [sum 2C][CC])
-__global__ void cond_embed_kernel(const float* __restrict__ cs, const int64_t* __restrict__ act,
-                                  const float* __restrict__ fourier_w, const float* __restrict__ act_emb,
-                                  float* __restrict__ e, int B, int CC, int T, int num_actions) {
+// cs != null: c_noise of sample n is cs[n][3] (written by the pack kernel).  cs == null: row r = (evaluation k, sample n) of a
+// batch of K sampler evaluations, c_noise computed from sig_all[k] (all denoising steps' conditioning in ONE launch: the sigma
+// schedule is host-known, diffusion_sampler.py:27, and the actions do not change inside sample()).
+__global__ void cond_embed_kernel(const float* __restrict__ cs, const float* __restrict__ sig_all, float sigma_data, float sigma_offset,
+                                  const int64_t* __restrict__ act, const float* __restrict__ fourier_w, const float* __restrict__ act_emb,
+                                  float* __restrict__ e, int rows, int B, int CC, int T, int num_actions, StackView sv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * CC) return;
-  const int n = i / CC, k = i - n * CC;
+  if (i >= rows * CC) return;
+  const int r = i / CC, k = i - r * CC;
+  const int n = r % B;
   const int half = CC / 2, E = CC / T;
-  const float c_noise = cs[n * 4 + 3];
+  const float c_noise = cs ? cs[n * 4 + 3] : edm_conditioners(sig_all[r / B], sigma_data, sigma_offset).w;
   const float t = __fmul_rn(6.283185307179586f, c_noise);
   const float f = __fmul_rn(t, fourier_w[k < half ? k : k - half]);
   const float four = k < half ? cosf(f) : sinf(f);
-  long long a = act[(size_t)n * T + k / E];
+  long long a;
+  if (sv.ring_T > 0) {
+    int ps = sv.head + k / E; if (ps >= sv.ring_T) ps -= sv.ring_T;
+    a = act[(size_t)ps * sv.act_slot_stride + (size_t)n * sv.act_batch_stride];
+  } else {
+    a = act[(size_t)n * T + k / E];
+  }
   a = a < 0 ? 0 : (a >= num_actions ? num_actions - 1 : a);
   e[i] = __fadd_rn(four, act_emb[(size_t)a * E + (k % E)]);
 }

@@ -506,7 +506,7 @@ struct PrepSrc {
 };
 struct PrepParams {
   PrepSrc s[2];
-  int B, Hs, Ws, ups, H, W;
+  int B, Hs, Ws, ups, H, W;   // ups: 0 none, 1 nearest-2x upsample, 2 zero insertion
   int mode;            // 0 raw, 1 AdaGroupNorm, 2 affine GroupNorm
   int act;             // SiLU
   const float* film;   // [B][film_stride]; scale at film_off + c, shift at film_off + film_ctot + c
@@ -576,7 +576,8 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
       if (pl + u * pstep < p.pos_per_block && pa < p.Qalloc) {
         meta[u] = -1;
         off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
-        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
+        // ups == 2: zero insertion (adjoint of the stride-2 subsample, blocks.py:96): only even (y, x) carry data
+        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B && (p.ups != 2 || ((x | y) & 1) == 0)) {
           const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
           const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
           v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);

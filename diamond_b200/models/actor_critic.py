@@ -67,6 +67,7 @@ class ActorCritic(nn.Module):
         self.env_loop = None
         self.loss_cfg = None
         self._h = None
+        self._h_dev = None
         self._wkey = None
         self._packed = None
         self._ws = None
@@ -117,62 +118,149 @@ class ActorCritic(nn.Module):
             self._wkey = wkey
         return self._h
 
-    # ------------------------------------------------------------------ reference surface
-    def predict_act_value(self, obs: Tensor, hx_cx: Tuple[Tensor, Tensor]) -> ActorCriticOutput:  # actor_critic.py:68-73
-        assert obs.ndim == 4
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "ActorCritic.predict_act_value with autograd (BPTT through the imagined rollout, SURVEY.md 8 a22/a23) is not "
-                "built yet; call under torch.no_grad()"
-            )
+    def _state_tensors(self):
+        return list(self.state_dict(keep_vars=True).values())
+
+    def grad_layout(self):
+        lib = _lib.lib()
+        h = self._native()
+        n = lib.dmd_actor_critic_num_tensors(h)
+        offs, nums = (C.c_longlong * n)(), (C.c_longlong * n)()
+        total = lib.dmd_actor_critic_grad_layout(h, offs, nums, n)
+        if total < 0:
+            raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
+        return list(offs), list(nums), int(total)
+
+    def _acquire_ws(self, nbytes: int, dev) -> Tensor:
+        pool = self.__dict__.setdefault("_ws_pool", [])
+        for i, ws in enumerate(pool):
+            if ws.numel() >= nbytes and ws.device == dev:
+                return pool.pop(i)
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def _release_ws(self, ws: Tensor) -> None:
+        pool = self.__dict__.setdefault("_ws_pool", [])
+        if len(pool) < 64:   # one workspace per live autograd node of the imagined rollout (15 steps + burn-in calls)
+            pool.append(ws)
+
+    def _native_forward(self, obs: Tensor, hx: Tensor, cx: Tensor, ws: Tensor):
         lib = _lib.lib()
         h = self._native()
         b = obs.size(0)
-        hx, cx = hx_cx
-        obs_, hx_, cx_ = obs.float().contiguous(), hx.float().contiguous(), cx.float().contiguous()
         logits = torch.empty(b, self.cfg.num_actions, device=obs.device)
         val = torch.empty(b, device=obs.device)
-        hx_o, cx_o = torch.empty_like(hx_), torch.empty_like(cx_)
-        need = lib.dmd_actor_critic_workspace_bytes(h, b)
-        if self._ws is None or self._ws.numel() < need:
+        hx_o, cx_o = torch.empty_like(hx), torch.empty_like(cx)
+        _lib.check(lib.dmd_actor_critic_forward(h, b, obs.data_ptr(), hx.data_ptr(), cx.data_ptr(), logits.data_ptr(),
+                                                val.data_ptr(), hx_o.data_ptr(), cx_o.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.current_stream()))
+        return logits, val, hx_o, cx_o
+
+    # ------------------------------------------------------------------ reference surface
+    def predict_act_value(self, obs: Tensor, hx_cx: Tuple[Tensor, Tensor]) -> ActorCriticOutput:  # actor_critic.py:68-73
+        assert obs.ndim == 4
+        lib = _lib.lib()
+        h = self._native()
+        hx, cx = hx_cx
+        obs_, hx_, cx_ = obs.float().contiguous(), hx.float().contiguous(), cx.float().contiguous()
+        need = lib.dmd_actor_critic_workspace_bytes(h, obs.size(0))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # one autograd node per call: the imagined rollout back-propagates through time across these nodes
+            params = [p for p in self.parameters()]
+            logits, val, hx_o, cx_o = _PredictActValueFn.apply(self, obs_, hx_, cx_, *params)
+            return ActorCriticOutput(logits, val, (hx_o, cx_o))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != obs.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=obs.device)
-        _lib.check(lib.dmd_actor_critic_forward(h, b, obs_.data_ptr(), hx_.data_ptr(), cx_.data_ptr(), logits.data_ptr(),
-                                                val.data_ptr(), hx_o.data_ptr(), cx_o.data_ptr(), self._ws.data_ptr(),
-                                                self._ws.numel(), _lib.current_stream()))
+        logits, val, hx_o, cx_o = self._native_forward(obs_, hx_, cx_, self._ws)
         return ActorCriticOutput(logits, val, (hx_o, cx_o))
 
     def forward(self) -> LossAndLogs:  # actor_critic.py:75-98
-        c = self.loss_cfg
-        _, act, rew, end, trunc, logits_act, val, val_bootstrap, _ = self.env_loop.send(c.backup_every)
-        d = Categorical(logits=logits_act)
-        entropy = d.entropy().mean()
-        lambda_returns = compute_lambda_returns(rew, end, trunc, val_bootstrap, c.gamma, c.lambda_)
-        loss_actions = (-d.log_prob(act) * (lambda_returns - val).detach()).mean()
-        loss_values = c.weight_value_loss * F.mse_loss(val, lambda_returns)
-        loss_entropy = -c.weight_entropy_loss * entropy
+        """REINFORCE with a lambda-return baseline over one imagined rollout of `backup_every` steps."""
+        cfg = self.loss_cfg
+        _, act, rew, end, trunc, logits, val, val_bootstrap, _ = self.env_loop.send(cfg.backup_every)
+        policy = Categorical(logits=logits)
+        entropy = policy.entropy().mean()
+        target = compute_lambda_returns(rew, end, trunc, val_bootstrap, cfg.gamma, cfg.lambda_)
+        advantage = (target - val).detach()
+        loss_actions = (-policy.log_prob(act) * advantage).mean()
+        loss_values = cfg.weight_value_loss * F.mse_loss(val, target)
+        loss_entropy = -cfg.weight_entropy_loss * entropy
         loss = loss_actions + loss_entropy + loss_values
-        metrics = {
+        logs = {
             "policy_entropy": entropy.detach() / math.log(2),
             "loss_actions": loss_actions.detach(),
             "loss_entropy": loss_entropy.detach(),
             "loss_values": loss_values.detach(),
             "loss_total": loss.detach(),
         }
-        return loss, metrics
+        return loss, logs
 
 
 @torch.no_grad()
 def compute_lambda_returns(rew: Tensor, end: Tensor, trunc: Tensor, val_bootstrap: Tensor, gamma: float, lambda_: float) -> Tensor:
-    """actor_critic.py:116-143: lambda-returns with sign-clipped rewards, episode ends and truncations."""
+    """Lambda-returns with sign-clipped rewards, episode ends and truncations (actor_critic.py:116-143).  CUDA inputs run in
+    one native kernel (one thread per environment walking time backwards, fp32 operations in the reference's order:
+    bit-identical); CPU inputs (host-logic tests only) evaluate the same recursion with torch ops."""
     assert rew.ndim == 2 and rew.size() == end.size() == trunc.size() == val_bootstrap.size()
-    rew = rew.sign()
-    end_or_trunc = (end + trunc).clip(max=1)
-    not_end, not_trunc = 1 - end, 1 - trunc
-    returns = rew + not_end * gamma * (not_trunc * (1 - lambda_) + trunc) * val_bootstrap
+    if rew.is_cuda:
+        b, t = rew.shape
+        out = torch.empty(b, t, dtype=torch.float32, device=rew.device)
+        _lib.check(_lib.lib().dmd_lambda_returns(rew.float().contiguous().data_ptr(), end.long().contiguous().data_ptr(),
+                                                 trunc.long().contiguous().data_ptr(), val_bootstrap.float().contiguous().data_ptr(),
+                                                 out.data_ptr(), b, t, float(gamma), float(lambda_), _lib.current_stream()))
+        return out
+    stop = (end + trunc).clip(max=1)
+    out = rew.sign() + (1 - end) * gamma * ((1 - trunc) * (1 - lambda_) + trunc) * val_bootstrap
     if lambda_ == 0:
-        return returns
-    last = val_bootstrap[:, -1]
-    for t in reversed(range(rew.size(1))):
-        returns[:, t] += end_or_trunc[:, t].logical_not() * gamma * lambda_ * last
-        last = returns[:, t]
-    return returns
+        return out
+    carry = val_bootstrap[:, -1]
+    for t in range(rew.size(1) - 1, -1, -1):
+        out[:, t] += stop[:, t].logical_not() * gamma * lambda_ * carry
+        carry = out[:, t]
+    return out
+
+
+class _PredictActValueFn(torch.autograd.Function):
+    """predict_act_value as one autograd node: forward = dmd_actor_critic_forward into a workspace that is kept until
+    backward = dmd_actor_critic_backward (gradients wrt hx, cx and every parameter; obs needs none)."""
+
+    @staticmethod
+    def forward(ctx, module, obs, hx, cx, *params):
+        lib = _lib.lib()
+        h = module._native()
+        ws = module._acquire_ws(lib.dmd_actor_critic_workspace_bytes(h, obs.size(0)), obs.device)
+        logits, val, hx_o, cx_o = module._native_forward(obs, hx.detach(), cx.detach(), ws)
+        ctx.module, ctx.ws, ctx.b = module, ws, obs.size(0)
+        ctx.save_for_backward(hx.detach(), cx.detach(), hx_o)
+        ctx.set_materialize_grads(False)
+        return logits, val, hx_o, cx_o
+
+    @staticmethod
+    def backward(ctx, g_logits, g_val, g_hx, g_cx):
+        lib = _lib.lib()
+        module = ctx.module
+        h = module._native()
+        hx, cx, hx_o = ctx.saved_tensors
+        dev = hx.device
+        offs, nums, total = module.grad_layout()
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        g_hx_in, g_cx_in = torch.empty_like(hx), torch.empty_like(cx)
+        need = lib.dmd_actor_critic_backward_scratch_bytes(h, ctx.b)
+        scratch = module.__dict__.get("_bwd_scratch")
+        if scratch is None or scratch.numel() < need or scratch.device != dev:
+            scratch = module.__dict__["_bwd_scratch"] = torch.empty(need, dtype=torch.uint8, device=dev)
+
+        def c(t):
+            return None if t is None else t.float().contiguous()
+
+        gl, gv, gh, gc = c(g_logits), c(g_val), c(g_hx), c(g_cx)
+        _lib.check(lib.dmd_actor_critic_backward(h, ctx.b, hx.data_ptr(), cx.data_ptr(), hx_o.data_ptr(), _lib.ptr(gl), _lib.ptr(gv),
+                                                 _lib.ptr(gh), _lib.ptr(gc), flat.data_ptr(), total, g_hx_in.data_ptr(),
+                                                 g_cx_in.data_ptr(), ctx.ws.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                                 _lib.current_stream()))
+        module._release_ws(ctx.ws)
+        index = {k: i for i, k in enumerate(module.state_dict().keys())}
+        grads = []
+        for name, p in module.named_parameters():
+            i = index[name]
+            grads.append(flat[offs[i]:offs[i] + nums[i]].view_as(p))
+        return (None, None, g_hx_in, g_cx_in, *grads)

@@ -109,7 +109,26 @@ class Denoiser(nn.Module):
         return den
 
     def forward(self, batch) -> LossAndLogs:  # denoiser.py:93-122
-        raise NotImplementedError(
-            "Denoiser.forward (training loss + backward through the native U-Net) is the next SURVEY.md section-8 row; "
-            "round 1 ships the inference / imagination path (denoise, DiffusionSampler.sample)"
-        )
+        """Training loss: for each autoregressive step, noise the target frame, run the native U-Net (autograd node
+        `_InnerModelFn`), regress the EDM target, and write the quantised denoised frame back so that the next step is
+        conditioned on the model's own output.  Same RNG draws, in the same order, as the reference (sigma, offset, noise)."""
+        if self.sample_sigma_training is None:
+            raise RuntimeError("call setup_training(SigmaDistributionConfig) first (denoiser.py:52)")
+        n_cond = self.cfg.inner_model.num_steps_conditioning
+        frames = batch.obs.clone()                     # (B, T, C, H, W); column n_cond + i is overwritten by step i
+        steps = frames.size(1) - n_cond
+        b, _, c, h, w = frames.shape
+        total = 0
+        for i in range(steps):
+            target_frame = frames[:, n_cond + i]
+            keep = batch.mask_padding[:, n_cond + i]
+            stack = frames[:, i:n_cond + i].reshape(b, n_cond * c, h, w)
+            sigma = self.sample_sigma_training(b, self.device)
+            noisy = self.apply_noise(target_frame, sigma, self.cfg.sigma_offset_noise)
+            cs = self.compute_conditioners(sigma)
+            out = self.compute_model_output(noisy, stack, batch.act[:, i:n_cond + i], cs)
+            wanted = (target_frame - cs.c_skip * noisy) / cs.c_out
+            total = total + torch.nn.functional.mse_loss(out[keep], wanted[keep])
+            frames[:, n_cond + i] = self.wrap_model_output(noisy, out, cs)
+        loss = total / steps
+        return loss, {"loss_denoising": loss.detach()}

@@ -41,37 +41,59 @@ class DiffusionSampler:
         self._sigmas_host = build_sigmas(cfg.num_steps_denoising, cfg.sigma_min, cfg.sigma_max, cfg.rho, torch.device("cpu"))
         self.sigmas = self._sigmas_host.to(denoiser.device)
         self.use_cuda_graph = True
+        self._n_sig = int(self._sigmas_host.numel())
+        self._sig_arr = (C.c_float * self._n_sig)(*self._sigmas_host.tolist())
+        self._sc = _lib.SamplerConfigC(self._n_sig, self._sig_arr, int(cfg.order), float(cfg.s_churn), float(cfg.s_tmin),
+                                       float(min(cfg.s_tmax, 3.0e38)), 1.0)
+        self._gamma = min(cfg.s_churn / (self._n_sig - 1), 2**0.5 - 1)
+        self._buf = {}   # persistent device buffers per (B, C, H, W): the native call (a CUDA graph) uses them in place
 
-    @torch.no_grad()
-    def sample(self, prev_obs: Tensor, prev_act: Tensor) -> Tuple[Tensor, List[Tensor]]:  # diffusion_sampler.py:31-58
+    def _buffers(self, b: int, t: int, c: int, h: int, w: int, device):
+        key = (b, t, c, h, w, device)
+        if key not in self._buf:
+            self._buf = {key: dict(
+                traj=torch.empty(self._n_sig, b, c, h, w, device=device),
+                eps=torch.zeros(self._n_sig - 1, b, c, h, w, device=device) if self._gamma > 0 else None,
+                obs=torch.empty(b, t * c, h, w, device=device), act=torch.empty(b, t, dtype=torch.long, device=device))}
+        return self._buf[key]
+
+    def _draw_noise(self, buf) -> None:
+        """RNG stream parity with the reference: x first (diffusion_sampler.py:36), then one eps per churned step (:42)."""
+        traj, eps = buf["traj"], buf["eps"]
+        traj[0].copy_(torch.randn(*traj.shape[1:], device=traj.device))
+        if eps is not None:
+            for i, sigma in enumerate(self._sigmas_host[:-1].tolist()):
+                if self.cfg.s_tmin <= sigma <= self.cfg.s_tmax:
+                    eps[i].copy_(torch.randn(*traj.shape[1:], device=traj.device) * self.cfg.s_noise)
+
+    def _run(self, obs: Tensor, act: Tensor, ring_head: int, buf, out_x, b: int, h: int, w: int) -> None:
         lib = _lib.lib()
         den = self.denoiser
         im = den.inner_model
-        device = prev_obs.device
-        b, t, c, h, w = prev_obs.size()
-        obs = prev_obs.reshape(b, t * c, h, w).float().contiguous()
-        act = prev_act.long().contiguous()
-        n_sig = int(self._sigmas_host.numel())
-        gamma_ = min(self.cfg.s_churn / (n_sig - 1), 2**0.5 - 1)
-        # RNG stream parity with the reference: x first, then one eps per step that churns (diffusion_sampler.py:36,42)
-        x0 = torch.randn(b, c, h, w, device=device)
-        eps = None
-        if gamma_ > 0:
-            eps = torch.zeros(n_sig - 1, b, c, h, w, device=device)
-            for i, sigma in enumerate(self._sigmas_host[:-1].tolist()):
-                if self.cfg.s_tmin <= sigma <= self.cfg.s_tmax:
-                    eps[i] = torch.randn(b, c, h, w, device=device) * self.cfg.s_noise
         hnd = im.native(den.cfg.sigma_data, den.cfg.sigma_offset_noise)
-        core = lib.dmd_denoiser_workspace_bytes(hnd, b, h, w)
-        img_bytes = b * c * h * w * 4
-        need = core + img_bytes * (n_sig + (n_sig - 1 if eps is not None else 0)) + 4096
-        ws = im.workspace(need)
-        sig_arr = (C.c_float * n_sig)(*self._sigmas_host.tolist())
-        sc = _lib.SamplerConfigC(n_sig, sig_arr, int(self.cfg.order), float(self.cfg.s_churn), float(self.cfg.s_tmin),
-                                 float(min(self.cfg.s_tmax, 3.0e38)), 1.0)
-        out_x = torch.empty(b, c, h, w, device=device)
-        traj = torch.empty(n_sig, b, c, h, w, device=device)
-        _lib.check(lib.dmd_sampler_sample(hnd, C.byref(sc), b, h, w, obs.data_ptr(), act.data_ptr(), x0.data_ptr(),
-                                          _lib.ptr(eps), out_x.data_ptr(), traj.data_ptr(), ws.data_ptr(), ws.numel(),
+        ws = im.workspace(lib.dmd_denoiser_workspace_bytes(hnd, b, h, w))
+        _lib.check(lib.dmd_sampler_sample(hnd, C.byref(self._sc), b, h, w, obs.data_ptr(), act.data_ptr(), ring_head,
+                                          buf["traj"].data_ptr(), _lib.ptr(buf["eps"]), _lib.ptr(out_x), ws.data_ptr(), ws.numel(),
                                           int(self.use_cuda_graph), _lib.current_stream()))
-        return out_x, list(traj.unbind(0))
+
+    @torch.no_grad()
+    def sample(self, prev_obs: Tensor, prev_act: Tensor) -> Tuple[Tensor, List[Tensor]]:  # diffusion_sampler.py:31-58
+        b, t, c, h, w = prev_obs.size()
+        buf = self._buffers(b, t, c, h, w, prev_obs.device)
+        buf["obs"].copy_(prev_obs.reshape(b, t * c, h, w))   # stable addresses: the captured graph is replayed as is
+        buf["act"].copy_(prev_act)
+        self._draw_noise(buf)
+        self._run(buf["obs"], buf["act"], -1, buf, None, b, h, w)
+        traj = buf["traj"].clone()                           # the caller owns what it gets; the buffers are reused next call
+        return traj[-1], list(traj.unbind(0))
+
+    @torch.no_grad()
+    def sample_ring(self, frames: Tensor, acts: Tensor, head: int, out_frame: Tensor) -> Tensor:
+        """The WorldModelEnv path: `frames` (T, B, C, H, W) / `acts` (T, B) are the environment's resident ring buffers with
+        logical slot k at physical slot (head + k) % T; the new frame is written straight into `out_frame` (a ring slot).
+        Nothing is staged or rolled.  Returns the trajectory buffer (num_sigmas, B, C, H, W), valid until the next call."""
+        t, b, c, h, w = frames.size()
+        buf = self._buffers(b, t, c, h, w, frames.device)
+        self._draw_noise(buf)
+        self._run(frames, acts, head, buf, out_frame, b, h, w)
+        return buf["traj"]

@@ -100,13 +100,41 @@ class InnerModel(nn.Module):
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return self._ws
 
+    # ------------------------------------------------------------------ training plumbing
+    def grad_layout(self):
+        """(offsets, numels, total) of the flat fp32 gradient buffer the native backward fills (state_dict order)."""
+        lib = _lib.lib()
+        h = self.native()
+        n = lib.dmd_denoiser_num_tensors(h)
+        offs, nums = (C.c_longlong * n)(), (C.c_longlong * n)()
+        total = lib.dmd_denoiser_grad_layout(h, offs, nums, n)
+        if total < 0:
+            raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
+        return list(offs), list(nums), int(total)
+
+    def acquire_train_workspace(self, nbytes: int) -> Tensor:
+        """A training workspace holds one forward's activations until its backward has run; an autoregressive
+        Denoiser.forward therefore holds several at once.  Buffers are pooled and reused across optimizer steps."""
+        dev = self.noise_emb.weight.device
+        pool = self.__dict__.setdefault("_tws_pool", [])
+        for i, ws in enumerate(pool):
+            if ws.numel() >= nbytes and ws.device == dev:
+                return pool.pop(i)
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def release_train_workspace(self, ws: Tensor) -> None:
+        pool = self.__dict__.setdefault("_tws_pool", [])
+        if len(pool) < 4:
+            pool.append(ws)
+
     # ------------------------------------------------------------------ reference surface
     def forward(self, noisy_next_obs: Tensor, c_noise: Tensor, obs: Tensor, act: Tensor) -> Tensor:  # inner_model.py:44-49
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "InnerModel.forward with autograd (denoiser training, SURVEY.md 8 a18) is not built yet; "
-                "call under torch.no_grad()"
-            )
+            # training: native forward that keeps its activations + native backward, behind one autograd node whose inputs
+            # are the leaf parameters (so .grad lands where configure_opt / DDP expect it, utils.py:105-106,129-166)
+            names = [k for k, _ in self.named_parameters()]
+            params = [p for _, p in self.named_parameters()]
+            return _InnerModelFn.apply(self, names, noisy_next_obs, c_noise, obs, act, *params)
         lib = _lib.lib()
         h = self.native()
         b, _, hh, ww = noisy_next_obs.shape
@@ -120,3 +148,43 @@ class InnerModel(nn.Module):
                                                obs_.data_ptr(), act_.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                                _lib.current_stream()))
         return out
+
+
+class _InnerModelFn(torch.autograd.Function):
+    """InnerModel.forward under autograd: forward = dmd_inner_model_forward_train (activations stay in the training
+    workspace), backward = dmd_denoiser_backward (all parameter gradients in one flat buffer, returned as views)."""
+
+    @staticmethod
+    def forward(ctx, module, names, noisy, c_noise, obs, act, *params):
+        lib = _lib.lib()
+        h = module.native()
+        b, _, hh, ww = noisy.shape
+        noisy_, obs_ = noisy.detach().float().contiguous(), obs.detach().float().contiguous()
+        cn = c_noise.detach().float().contiguous().reshape(-1)
+        act_ = act.long().contiguous()
+        out = torch.empty_like(noisy_)
+        ws = module.acquire_train_workspace(lib.dmd_denoiser_train_workspace_bytes(h, b, hh, ww))
+        _lib.check(lib.dmd_inner_model_forward_train(h, b, hh, ww, noisy_.data_ptr(), cn.data_ptr(), int(cn.numel() == 1),
+                                                     obs_.data_ptr(), act_.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     _lib.current_stream()))
+        ctx.module, ctx.names, ctx.shape, ctx.ws, ctx.keep = module, names, (b, hh, ww), ws, (noisy_, obs_, cn, act_)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.lib()
+        module = ctx.module
+        h = module.native()
+        b, hh, ww = ctx.shape
+        offs, nums, total = module.grad_layout()
+        flat = torch.empty(total, dtype=torch.float32, device=grad_out.device)
+        g = grad_out.float().contiguous()
+        _lib.check(lib.dmd_denoiser_backward(h, b, hh, ww, g.data_ptr(), flat.data_ptr(), total, ctx.ws.data_ptr(), _lib.current_stream()))
+        index = {k: i for i, k in enumerate(module.state_dict().keys())}
+        grads = []
+        for name, p in zip(ctx.names, module.parameters()):
+            i = index[name]
+            grads.append(flat[offs[i]:offs[i] + nums[i]].view_as(p))
+        module.release_train_workspace(ctx.ws)
+        module.last_flat_grad = flat   # one contiguous buffer: what a data-parallel step all-reduces in a single collective
+        return (None, None, None, None, None, None, *grads)

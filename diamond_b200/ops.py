@@ -149,3 +149,39 @@ def attn_fwd(x: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, wqkv: Ten
                                        wqkv.data_ptr(), bqkv.data_ptr(), wout.data_ptr(), bout.data_ptr(), out.data_ptr(),
                                        _lib.ptr(ostats), b, h * w, c, gs, eps, _lib.current_stream()))
     return out, ostats
+
+
+def pack_conv_weight_T(w: Tensor, ci_off: int = 0, cin_k: Optional[int] = None) -> Tuple[Tensor, int, int]:
+    """Weights of the dgrad conv (= fprop on dL/dy with transposed, tap-flipped weights) for the input channels
+    [ci_off, ci_off + cin_k) of a torch weight [Cout][Cin][k][k]; returns (packed, CinP = round16(Cout), CoutP = round16(cin_k))."""
+    _cuda(w)
+    cout, cin, kh, kw = w.shape
+    cin_k = cin - ci_off if cin_k is None else cin_k
+    cin_p, cout_p = round_up(cout, 16), round_up(cin_k, 16)
+    out = torch.empty(kh * kw * cin_p * cout_p, device=w.device, dtype=torch.float16)
+    _lib.check(_lib.lib().dmd_pack_conv_weight_dgrad(w.data_ptr(), out.data_ptr(), cout, cin, ci_off, cin_k, kh * kw, _lib.current_stream()))
+    return out, cin_p, cout_p
+
+
+_partial = {}
+
+
+def conv2d_wgrad(grad_op: Tensor, cg: int, act_op: Tensor, ca: int, b: int, h: int, w: int, cout: int, cin: int, taps: int = 9, *,
+                 dw: Optional[Tensor] = None, cin_tot: Optional[int] = None, ci_off: int = 0, inv_scale: Optional[Tensor] = None,
+                 accumulate: bool = False, debug: int = 0) -> Tensor:
+    """tcgen05 weight gradient from two PLC16 operands (dL/dy with `cg` stored channels, conv input with `ca`)."""
+    _cuda(grad_op, act_op)
+    lib = _lib.lib()
+    cin_tot = cin if cin_tot is None else cin_tot
+    if dw is None:
+        dw = torch.zeros(cout, cin_tot, taps, device=grad_op.device, dtype=torch.float32)
+    key = grad_op.device.index
+    if key not in _partial:
+        _partial[key] = torch.empty(lib.dmd_wgrad_partial_bytes(), dtype=torch.uint8, device=grad_op.device)
+    part = _partial[key]
+    d = _lib.WgradDesc()
+    d.grad, d.act, d.Cg, d.Ca, d.B, d.H, d.W, d.taps = grad_op.data_ptr(), act_op.data_ptr(), cg, ca, b, h, w, taps
+    d.dW, d.Cout, d.Cin, d.CinTot, d.ci_off = dw.data_ptr(), cout, cin, cin_tot, ci_off
+    d.inv_scale, d.accumulate, d.partial, d.partial_bytes, d.debug = _lib.ptr(inv_scale), int(accumulate), part.data_ptr(), part.numel(), debug
+    _lib.check(lib.dmd_conv2d_wgrad(C.byref(d), _lib.current_stream()))
+    return dw

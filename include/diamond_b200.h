@@ -52,7 +52,7 @@ typedef struct dmd_prep_desc {
   const float* src1;     /* NHWC [B][Hs][Ws][C1] or NULL */
   int C0, C1;            /* multiples of 8 */
   int B, Hs, Ws;
-  int upsample;
+  int upsample;          /* 0 none ; 1 nearest-2x (blocks.py:109) ; 2 zero insertion (adjoint of the stride-2 subsample) */
   int mode;              /* 0 raw ; 1 AdaGroupNorm ; 2 affine GroupNorm */
   int silu;
   const double* stats0;  /* [B][C0/gs0][2] (sum, sumsq) */
@@ -104,6 +104,32 @@ typedef struct dmd_conv_desc {
 } dmd_conv_desc;
 
 int dmd_conv2d_fprop(const dmd_conv_desc* d, void* stream);
+
+/* Backward-data of nn.Conv2d = dmd_conv2d_fprop on dL/dy with the weights transposed and the taps flipped: packs
+ * w'[ci][co][t'] = w[co][ci_off + ci][taps-1-t'] of a torch weight [CoutF][CinTotF][k][k] for the CinK input channels starting
+ * at ci_off (one call per source of a channel concat) into [taps][round16(CoutF)/8][round16(CinK)][8] fp16. */
+int dmd_pack_conv_weight_dgrad(const float* w, void* wpk, int CoutF, int CinTotF, int ci_off, int CinK, int taps, void* stream);
+
+/* Backward-filter of nn.Conv2d (torch autograd conv2d_weight; reference forward src/models/blocks.py:18-19,96,109-110) on
+ * tcgen05: dW[co][ci_off+ci][t] (+)= inv_scale * sum_q GY[q][co] * X[q + o_t][ci] over the padded-linear positions of the
+ * two PLC16 operands (layout and kernel: diamond_b200/csrc/wgrad_tc.cuh).  Deterministic: per-CTA partial sums are reduced in
+ * a fixed order.  A stride-2 conv passes its gradient zero-inserted (dmd_prep_desc.upsample = 2) at the conv INPUT size. */
+typedef struct dmd_wgrad_desc {
+  const void* grad;      /* PLC16 operand of dL/dy: Cg stored channels (multiple of 8, <= 64), Cout real */
+  const void* act;       /* PLC16 operand of the conv input: Ca stored channels (16 / 32 / 64), Cin real */
+  int Cg, Ca;
+  int B, H, W;           /* conv input size */
+  int taps;              /* 9 or 1 */
+  float* dW;             /* torch layout [Cout][CinTot][taps] fp32 */
+  int Cout, Cin, CinTot, ci_off;
+  const float* inv_scale; /* device scalar multiplied into the result, or NULL */
+  int accumulate;        /* dW += instead of dW = */
+  void* partial;         /* workspace of dmd_wgrad_partial_bytes() */
+  size_t partial_bytes;
+  int debug;             /* bring-up only; 0 */
+} dmd_wgrad_desc;
+size_t dmd_wgrad_partial_bytes(void);
+int dmd_conv2d_wgrad(const dmd_wgrad_desc* d, void* stream);
 
 /* Host-only twins of dmd_conv2d_fprop / dmd_prep_act: run exactly the same validation and planning, touch neither the
  * device nor the pointed-to memory (pointers are only tested for NULL), and report the launch plan.  They make the
@@ -176,6 +202,22 @@ int dmd_inner_model_forward(dmd_denoiser* h, int B, int H, int W, const float* n
                             int c_noise_is_scalar, const float* obs_rescaled, const int64_t* act, float* out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Training (Denoiser.forward + loss.backward(), src/models/diffusion/denoiser.py:93-122, src/trainer.py:365-366).
+ * dmd_inner_model_forward_train = dmd_inner_model_forward that keeps every activation (and the GroupNorm statistics) in the
+ * training workspace; dmd_denoiser_backward consumes them: given dL/d(model output) (B,C,H,W) it writes the gradient of
+ * EVERY parameter into one flat fp32 buffer (16-byte aligned slices, layout from dmd_denoiser_grad_layout, state_dict
+ * order; buffers such as noise_emb.weight get zeros).  Convolutions run on tcgen05 (dgrad = fprop with transposed weights,
+ * wgrad = dmd_conv2d_wgrad), gradients carry a power-of-two loss scale chosen from max|grad_out| on the device.  The flat
+ * buffer is what a data-parallel step all-reduces in ONE collective (utils.py:105-106 wraps each model in DDP instead). */
+size_t dmd_denoiser_train_workspace_bytes(const dmd_denoiser* h, int B, int H, int W);
+/* offsets / numels: n = dmd_denoiser_num_tensors entries (floats); returns the total length of the flat buffer. */
+long long dmd_denoiser_grad_layout(const dmd_denoiser* h, long long* offsets, long long* numels, int n);
+int dmd_inner_model_forward_train(dmd_denoiser* h, int B, int H, int W, const float* noisy_rescaled, const float* c_noise,
+                                  int c_noise_is_scalar, const float* obs_rescaled, const int64_t* act, float* out,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+int dmd_denoiser_backward(dmd_denoiser* h, int B, int H, int W, const float* grad_out, float* grads, long long grads_numel,
+                          void* workspace, void* stream);
+
 typedef struct dmd_sampler_config {
   int num_sigmas;               /* len(self.sigmas) = num_steps_denoising + 1, last one 0 */
   const float* sigmas_host;     /* host array, fp32 values of DiffusionSampler.sigmas */
@@ -183,17 +225,25 @@ typedef struct dmd_sampler_config {
   float s_churn, s_tmin, s_tmax, s_noise;
 } dmd_sampler_config;
 
-/* DiffusionSampler.sample.  x0: the initial randn (B,C,H,W) (diffusion_sampler.py:36) and eps: churn noise
- * (num_steps,B,C,H,W) or NULL are drawn by the CALLER with torch so that RNG streams match the reference.
- * out_x (B,C,H,W); out_traj (num_sigmas,B,C,H,W) or NULL. */
+/* DiffusionSampler.sample (src/models/diffusion/diffusion_sampler.py:31-58), whole loop in one call, replayed as a CUDA graph.
+ * Every buffer is used IN PLACE (no staging copies; a graph is cached per distinct set of addresses):
+ *   traj  (num_sigmas, B, C, H, W): slot 0 holds the initial x ~ N(0,1) on entry (drawn by the CALLER with torch so that RNG
+ *         streams match the reference, :36); slot i+1 receives the iterate after step i (the reference's `trajectory`).
+ *   eps   (num_steps, B, C, H, W) churn noise (:42) or NULL.
+ *   out_x (B, C, H, W) or NULL: additionally receives the final iterate (e.g. a slot of the caller's frame ring).
+ *   ring_head = -1: prev_obs (B, T*C, H, W), prev_act (B, T) as the reference passes them.
+ *   ring_head >= 0: the WorldModelEnv's resident buffers -- prev_obs = frames (T, B, C, H, W), prev_act = actions (T, B), where
+ *         LOGICAL slot k (0 = oldest) is physical slot (ring_head + k) % T: the per-step `roll` of both buffers
+ *         (src/envs/world_model_env.py:74-75) becomes an index increment.
+ * The conditioning path (Fourier + action embedding -> MLP -> all FiLM linears) of all denoising steps is evaluated once, up
+ * front: the sigma schedule is host-known (:27) and the actions are fixed during a call. */
 int dmd_sampler_sample(dmd_denoiser* h, const dmd_sampler_config* sc, int B, int H, int W, const float* prev_obs,
-                       const int64_t* prev_act, const float* x0, const float* eps, float* out_x, float* out_traj,
-                       void* workspace, size_t workspace_bytes, int use_graph, void* stream);
+                       const int64_t* prev_act, int ring_head, float* traj, const float* eps, float* out_x, void* workspace,
+                       size_t workspace_bytes, int use_graph, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Actor-critic executor: ActorCritic.predict_act_value (src/models/actor_critic.py:68-73) = ActorCriticEncoder
  * (:101-113: Conv3x3 + [SmallResBlock (blocks.py:116-123), MaxPool2d]*) -> flatten -> LSTMCell -> actor / critic heads.
- * Inference (no autograd) only in this round.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct dmd_actor_critic_config {
   int lstm_dim;
@@ -217,6 +267,24 @@ size_t dmd_actor_critic_workspace_bytes(const dmd_actor_critic* h, int B);
 int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float* obs, const float* hx_in, const float* cx_in,
                              float* logits, float* val, float* hx_out, float* cx_out, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* ---- Actor-critic training: ActorCritic.predict_act_value under autograd (src/models/actor_critic.py:68-73; the imagined
+ * rollout calls it with grad, src/coroutines/env_loop.py:31,57, and src/trainer.py:366 back-propagates through time).
+ * dmd_actor_critic_forward leaves every activation in its workspace; ONE dmd_actor_critic_backward call is one node of the
+ * BPTT graph: given the gradients wrt (logits, val, hx_out, cx_out) (any may be NULL = zero) it writes the gradients wrt
+ * (hx_in, cx_in) and the gradient of every parameter into a flat fp32 buffer (layout: dmd_actor_critic_grad_layout).
+ * `workspace` is the forward's (untouched since); `scratch` is transient and may be shared by all nodes of a stream. */
+size_t dmd_actor_critic_backward_scratch_bytes(const dmd_actor_critic* h, int B);
+long long dmd_actor_critic_grad_layout(const dmd_actor_critic* h, long long* offsets, long long* numels, int n);
+int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                              const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx, float* grads,
+                              long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace, void* scratch,
+                              size_t scratch_bytes, void* stream);
+
+/* compute_lambda_returns (src/models/actor_critic.py:116-143): rew / val_bootstrap fp32 [B][T], end / trunc int64 [B][T] ->
+ * out fp32 [B][T]; one thread per environment walks time backwards; bit-identical to the reference's torch expression. */
+int dmd_lambda_returns(const float* rew, const int64_t* end, const int64_t* trunc, const float* val_bootstrap, float* out, int B,
+                       int T, double gamma, double lambda_, void* stream);
 
 #ifdef __cplusplus
 }

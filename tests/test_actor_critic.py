@@ -40,7 +40,7 @@ def test_actor_critic_mirror_state_dict_and_init():
     assert sum(p.numel() for p in ac.parameters()) == 3_229_637
     assert float(ac.actor_linear.weight.abs().sum()) == 0 and float(ac.critic_linear.weight.abs().sum()) == 0
     assert torch.all(ac.lstm.bias_ih[512:1024] == 1) and float(ac.lstm.bias_hh.abs().sum()) == 0
-    with pytest.raises(NotImplementedError):  # training through the policy is not built this round
+    with pytest.raises(RuntimeError):  # no CPU route: the native executor refuses non-CUDA parameters
         ac.predict_act_value(torch.zeros(1, 3, 64, 64), (torch.zeros(1, 512), torch.zeros(1, 512)))
 
 

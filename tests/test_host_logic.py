@@ -59,9 +59,33 @@ def test_sigma_schedule_matches_reference_values():
     assert DiffusionSamplerConfig(3).order == 1
 
 
-def test_training_forward_is_explicitly_unbuilt_and_cpu_is_rejected():
+def test_training_needs_setup_and_cpu_is_rejected():
     den = _denoiser(O.InnerCfg())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):  # denoiser.py:52: setup_training first
         den(None)
     with pytest.raises(RuntimeError):  # no CPU fallback: the native executor refuses non-CUDA parameters
         den.denoise(torch.zeros(1, 3, 64, 64), torch.ones(1), torch.zeros(1, 12, 64, 64), torch.zeros(1, 4, dtype=torch.long))
+    from diamond_b200.models.diffusion import SigmaDistributionConfig
+
+    den.setup_training(SigmaDistributionConfig(-0.4, 1.2, 2e-3, 20))
+    from types import SimpleNamespace
+
+    batch = SimpleNamespace(obs=torch.zeros(2, 5, 3, 64, 64), act=torch.zeros(2, 5, dtype=torch.long), mask_padding=torch.ones(2, 5, dtype=torch.bool))
+    with pytest.raises(RuntimeError):  # the training forward is native too: CPU tensors are refused, not silently computed
+        den(batch)
+
+
+def test_synthetic_generators_match_the_oracle_rule():
+    """diamond_b200.synthetic (used by bench.py / smoke for the PRODUCT path) and the oracle's seeded weights agree, so the
+    GPU tests can compare a model initialised by one with the oracle evaluated on the other."""
+    from diamond_b200.synthetic import frame_stacks, randomize_module_
+
+    inner = O.InnerCfg(depths=[1, 1, 1, 1])
+    den = _denoiser(inner)
+    randomize_module_(den.inner_model, 42)
+    sd = O.seeded_state_dict(O.inner_model_shapes(inner), 42)
+    for k, v in den.inner_model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    obs, act, x0 = frame_stacks(3, 4, 3, 64, 64, 4, 7)
+    o2, a2, x2 = O.synthetic_inputs(3, inner, 64, 64, 7)
+    assert torch.equal(obs, o2) and torch.equal(act, a2) and torch.equal(x0, x2)
