@@ -345,6 +345,86 @@ def conv_traffic_from_profile():
     return None, None
 
 
+def train_block(dev, world, rank, batch, steps=5, warmup=2):
+    """cfg 2 of BASELINE.json: denoiser training step (Denoiser.forward + backward on the native path, ONE flat-buffer NCCL
+    all-reduce of the 17.6 MB gradient when world > 1, clip + AdamW as src/trainer.py:365-378), batch `batch` per GPU,
+    frame-stack 4 + 1 autoregressive step, synthetic frames.  Returns samples/s (whole job) and the time split."""
+    import torch
+    import torch.distributed as dist
+
+    from diamond_b200.models.diffusion import Denoiser, DenoiserConfig, InnerModelConfig, SigmaDistributionConfig
+    from diamond_b200.synthetic import frame_stacks, randomize_module_
+    from diamond_b200.utils import allreduce_native_gradients
+
+    den = Denoiser(DenoiserConfig(InnerModelConfig(3, 4, 256, [2, 2, 2, 2], [64] * 4, [0] * 4, 4), 0.5, 0.3))
+    randomize_module_(den.inner_model, 2024)
+    den = den.to(dev).train()
+    den.setup_training(SigmaDistributionConfig(-0.4, 1.2, 2e-3, 20))
+    opt = torch.optim.AdamW(den.parameters(), lr=1e-4, weight_decay=1e-2, eps=1e-8)
+    obs, act, _ = frame_stacks(batch, 5, 3, 64, 64, 4, 300 + rank)
+
+    class B_:
+        pass
+
+    b = B_()
+    b.obs, b.act, b.mask_padding = obs.to(dev), act.to(dev), torch.ones(batch, 5, dtype=torch.bool, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_fb = t_ar = t_opt = 0.0
+    for it in range(warmup + steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = den(b)
+        loss.backward()
+        e1.record()
+        ncoll = allreduce_native_gradients(den.inner_model)
+        e2.record()
+        torch.nn.utils.clip_grad_norm_(den.parameters(), 1.0)
+        opt.step()
+        e3.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            t_fb += e0.elapsed_time(e1); t_ar += e1.elapsed_time(e2); t_opt += e2.elapsed_time(e3)
+    tot = max_over_ranks([t_fb + t_ar + t_opt, t_fb, t_ar, t_opt], dev)
+    ms = tot[0] / steps
+    gflop = 3 * 6.0888 * batch  # fwd + dgrad + wgrad (SURVEY.md 8d: 18.27 GFLOP / sample / AR step)
+    return {"workload": "Denoiser.forward + backward + gradient all-reduce + clip + AdamW (cfg 2), batch %d per GPU, 1 AR step" % batch,
+            "value": batch * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "fwd_bwd_ms": tot[1] / steps,
+            "allreduce_ms": tot[2] / steps, "clip_adamw_ms": tot[3] / steps, "collectives_per_step": ncoll if world > 1 else 0,
+            "allreduce_bytes": int(sum(p.numel() for p in den.parameters()) * 4), "loss": float(loss),
+            "achieved_tflops_per_gpu": gflop / (tot[1] / steps) / 1e3 * 1e0, "steps": steps, "warmup": warmup}
+
+
+def wgrad_roofline(dev, batch, peaks):
+    """tcgen05 wgrad kernel, 3x3 64->64 at 64x64 over `batch` images (the dominant backward-filter shape), timed alone."""
+    import torch
+
+    from diamond_b200 import ops
+
+    x = torch.randn(batch, 64, 64, 64, device=dev)
+    g = torch.randn(batch, 64, 64, 64, device=dev)
+    xo, go = ops.prep_act(x)[0], ops.prep_act(g)[0]
+    dw = torch.zeros(64, 64, 9, device=dev)
+    for _ in range(3):
+        ops.conv2d_wgrad(go, 64, xo, 64, batch, 64, 64, 64, 64, 9, dw=dw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        ops.conv2d_wgrad(go, 64, xo, 64, batch, 64, 64, 64, 64, 9, dw=dw)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    flops = 2.0 * 576 * 64 * 4096 * batch
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    return {"kernel": "wgrad_tc_kernel + fixed-order reduce, 3x3 64->64 @64x64, %d images" % batch, "us_per_launch": us,
+            "achieved": flops / (us * 1e-6) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (us * 1e-6) / 1e12 / peak}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -421,6 +501,12 @@ def run_native(args):
 
     dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms], dev)
     frames = B * args.steps * world
+    train = None
+    if not args.skip_train:
+        try:
+            train = train_block(dev, world, rank, args.train_batch)
+        except Exception as e:  # noqa: BLE001
+            train = {"error": repr(e)[:300]}
     if rank == 0:
         peaks, peaks_src = load_peaks()
         roof = conv_roofline(dev, B, peaks, peaks_src)
@@ -448,6 +534,12 @@ def run_native(args):
                                     "(not max-per-element); outputs behind the truncating uint8 quantiser: never more than one level off",
                        "tests": "tests/test_gpu_denoiser.py (B=1, 2, 3, 5 and the benchmarked B=32)"},
         }
+        if train is not None:
+            line["train_denoiser"] = train
+            try:
+                line["train_denoiser"]["wgrad_roofline"] = wgrad_roofline(dev, min(args.train_batch, 64), peaks)
+            except Exception as e:  # noqa: BLE001
+                line["train_denoiser"]["wgrad_roofline"] = {"error": repr(e)[:200]}
         if gpu_base is not None:
             line["gpu_baseline"] = gpu_base
             for k in ("eager", "compiled_reduce_overhead"):
@@ -472,6 +564,8 @@ def main():
     ap.add_argument("--envs", type=int, default=32, help="imagined environments per GPU (config/trainer.yaml actor_critic batch 32)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="development runs: omit the (minutes-long) cpu_baseline leg")
+    ap.add_argument("--skip-train", action="store_true", help="omit the denoiser-training block (cfg 2)")
+    ap.add_argument("--train-batch", type=int, default=256, help="denoiser training batch per GPU (config/trainer.yaml: 32; BASELINE cfg 2: 256)")
     ap.add_argument("--skip-gpu-baseline", action="store_true", help="omit the reference-GPU-path leg (eager + torch.compile of the oracle port)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -45,6 +45,13 @@ class ActorCriticConfigC(C.Structure):
     ]
 
 
+class RewEndConfigC(C.Structure):
+    _fields_ = [
+        ("lstm_dim", _i), ("img_channels", _i), ("img_size", _i), ("cond_channels", _i), ("num_levels", _i),
+        ("depths", _i * DMD_MAX_LEVELS), ("channels", _i * DMD_MAX_LEVELS), ("attn_depths", _i * DMD_MAX_LEVELS), ("num_actions", _i),
+    ]
+
+
 class SamplerConfigC(C.Structure):
     _fields_ = [
         ("num_sigmas", _i), ("sigmas_host", C.POINTER(_f)), ("order", _i),
@@ -104,6 +111,13 @@ SIGNATURES = {
     "dmd_actor_critic_backward_scratch_bytes": (_sz, [_vp, _i]),
     "dmd_actor_critic_grad_layout": (C.c_longlong, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
     "dmd_actor_critic_backward": (_i, [_vp, _i] + [_vp] * 8 + [C.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmd_rew_end_create": (_vp, [C.POINTER(RewEndConfigC)]),
+    "dmd_rew_end_destroy": (None, [_vp]),
+    "dmd_rew_end_num_tensors": (_i, [_vp]),
+    "dmd_rew_end_packed_bytes": (_sz, [_vp]),
+    "dmd_rew_end_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp]),
+    "dmd_rew_end_workspace_bytes": (_sz, [_vp, _i]),
+    "dmd_rew_end_predict": (_i, [_vp, _i, _i] + [_vp] * 9 + [_vp, _sz, _vp]),
     "dmd_lambda_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_double, C.c_double, _vp]),
 }
 

@@ -764,6 +764,36 @@ struct PlanBuilder {
     return a;
   }
 
+  // RewEndEncoder.forward (rew_end_model.py:127-132): conv_in, then per level [Downsample] + ResBlocks, then two attention
+  // ResBlocks; the same blocks as the U-Net, conditioned on the action embedding.  Output: pl->feat (NHWC, last level).
+  int build_rew_end(const std::vector<std::vector<ResBlockW>>& blocks, const std::vector<ConvW>& downs, const ConvW& conv_in, Tens* feat) {
+    const dmd_denoiser_config& c = h->cfg;
+    const int L = c.num_levels, B = pl->B, H = pl->H, W = pl->W;
+    if (H % (1 << (L - 1)) || W % (1 << (L - 1))) return fail("rew_end: H=%d W=%d must be multiples of %d", H, W, 1 << (L - 1));
+    int cmax = 16;
+    for (int i = 0; i < L; ++i) cmax = c.channels[i] > cmax ? c.channels[i] : cmax;
+    const size_t slot_bytes = (plc16_bytes(B, H, W, cmax) + 255) & ~(size_t)255;
+    for (int i = 0; i < kScratchSlots; ++i) pl->scratch[i] = (uint8_t*)bump->take(slot_bytes);
+    pl->scratch_next = 0;
+    pl->CP_in = conv_in.c0_store;
+    pl->xin = (float*)bump->take((size_t)B * H * W * pl->CP_in * 4);
+    pl->cond = (float*)bump->take((size_t)B * c.cond_channels * 4);
+    pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
+    Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
+    Tens x = tensor(c.channels[0], H, W, true);
+    conv(conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true), false, 1, nullptr, x, true);
+    for (int i = 0; i <= L; ++i) {
+      if (i > 0 && i < L) {
+        Tens xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true);
+        conv(downs[i], prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 2, nullptr, xd, true);
+        x = xd;
+      }
+      for (auto& rb : blocks[i]) x = resblock(rb, x, nullptr);
+    }
+    *feat = x;
+    return err;
+  }
+
   int build() {
     const dmd_denoiser_config& c = h->cfg;
     const int L = c.num_levels, B = pl->B, H = pl->H, W = pl->W;
@@ -1902,6 +1932,205 @@ extern "C" int dmd_lambda_returns(const float* rew, const int64_t* end, const in
   DMD_CHECK(rew && end && trunc && val_bootstrap && out && B > 0 && T > 0, "lambda_returns: bad arguments");
   lambda_returns_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, (const long long*)end, (const long long*)trunc, val_bootstrap, out, B, T,
                                                                          (float)gamma, (float)lambda_, (float)(1.0 - lambda_));
+  DMD_LAUNCH_OK();
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- reward / termination model
+// RewEndModel.predict_rew_end (src/models/rew_end_model.py:42-55): runs once per imagined step between the
+// sampler and the policy (world_model_env.py:97), and over the burn-in frames of every fresh episode (:120-129).
+//   encoder (conv_in + ResBlocks at C = 32 conditioned on the action embedding + two attention ResBlocks) -> (b t) features
+//   -> single-layer LSTM over time -> Linear / SiLU / Linear head -> 3 reward logits + 2 termination logits.
+// Rows are processed TIME-MAJOR (row = k * b + n) so that every LSTM step reads b contiguous feature rows.
+struct dmd_rew_end {
+  dmd_rew_end_config cfg;
+  dmd_denoiser core;     // parameter pointers / packed weights / FiLM table / plan of the encoder (reuses the U-Net block executor)
+  ConvW conv_in;
+  std::vector<std::vector<ResBlockW>> blocks;
+  std::vector<ConvW> downs;
+  int i_actemb = 0, i_wih = 0, i_whh = 0, i_bih = 0, i_bhh = 0, i_h0w = 0, i_h0b = 0, i_h2w = 0;
+  int feat_c = 0, feat_hw = 0;
+  Tens feat;
+  int planB = 0; void* plan_ws = nullptr;
+  float *x_gates = nullptr, *y = nullptr, *hid = nullptr, *logits_tm = nullptr, *hc[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+__global__ void pack_rew_end_input_kernel(const float* __restrict__ obs, const float* __restrict__ next_obs, const int64_t* __restrict__ act,
+                                          const float* __restrict__ act_emb, float* __restrict__ xin, float* __restrict__ cond, int b, int t,
+                                          int C, int CP, int HW, int CC, int num_actions) {
+  // row r = k * b + n (time-major)  <-  obs[n][k], next_obs[n][k], act[n][k]
+  const int r = blockIdx.y, k = r / b, n = r - k * b;
+  const size_t src = ((size_t)n * t + k) * C * HW;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {
+    long long a = act[(size_t)n * t + k];
+    a = a < 0 ? 0 : (a >= num_actions ? num_actions - 1 : a);
+    for (int j = threadIdx.x; j < CC; j += blockDim.x) cond[(size_t)r * CC + j] = act_emb[(size_t)a * CC + j];
+  }
+  if (pix >= HW) return;
+  float* o = xin + ((size_t)r * HW + pix) * CP;
+  for (int ch = 0; ch < CP; ++ch) {
+    float v = 0.f;
+    if (ch < C) v = obs[src + (size_t)ch * HW + pix];
+    else if (ch < 2 * C) v = next_obs[src + (size_t)(ch - C) * HW + pix];
+    o[ch] = v;
+  }
+}
+// logits_tm [t*b][5] (time-major) -> rew [b][t][3], end [b][t][2]
+__global__ void split_logits_kernel(const float* __restrict__ tm, float* __restrict__ rew, float* __restrict__ end, int b, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b * t) return;
+  const int n = i / t, k = i - n * t;
+  const float* s = tm + ((size_t)k * b + n) * 5;
+  rew[(size_t)i * 3] = s[0]; rew[(size_t)i * 3 + 1] = s[1]; rew[(size_t)i * 3 + 2] = s[2];
+  end[(size_t)i * 2] = s[3]; end[(size_t)i * 2 + 1] = s[4];
+}
+
+int rew_end_layout(dmd_rew_end* h, int B, int H, int W, uint8_t* base, size_t* total) {
+  dmd_denoiser* core = &h->core;
+  Plan& pl = core->plan;
+  pl.train = false; pl.B = B; pl.H = H; pl.W = W; pl.ops.clear();
+  Bump b0{nullptr}, s0{nullptr};
+  Tens feat;
+  { Plan tmp; tmp.B = B; tmp.H = H; tmp.W = W; PlanBuilder pb{core, &tmp, &b0, &s0}; if (pb.build_rew_end(h->blocks, h->downs, h->conv_in, &feat)) return 1; }
+  const size_t stats_bytes = (s0.off + 255) & ~(size_t)255;
+  Bump sb{base}, bb{base ? base + stats_bytes : nullptr};
+  if (base) {
+    pl.base = base; pl.stats = (double*)base; pl.stats_bytes = stats_bytes;
+    PlanBuilder pb{core, &pl, &bb, &sb};
+    if (pb.build_rew_end(h->blocks, h->downs, h->conv_in, &h->feat)) return 1;
+  } else bb.off = b0.off;
+  const int D = h->cfg.lstm_dim;
+  h->x_gates = (float*)bb.take((size_t)B * 4 * D * 4);
+  h->y = (float*)bb.take((size_t)B * D * 4); h->hid = (float*)bb.take((size_t)B * D * 4);
+  h->logits_tm = (float*)bb.take((size_t)B * 5 * 4);
+  h->hc[0] = (float*)bb.take((size_t)B * D * 4); h->hc[1] = (float*)bb.take((size_t)B * D * 4);
+  if (total) *total = stats_bytes + bb.off + 512;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" dmd_rew_end* dmd_rew_end_create(const dmd_rew_end_config* cfg) {
+  if (!cfg || cfg->num_levels < 1 || cfg->num_levels >= DMD_MAX_LEVELS) { fail("rew_end_create: bad config"); return nullptr; }
+  if (cfg->cond_channels % 32 || cfg->cond_channels > 256) { fail("rew_end_create: cond_channels must be a multiple of 32, <= 256"); return nullptr; }
+  for (int i = 0; i < cfg->num_levels; ++i)
+    if (cfg->channels[i] % 32 || cfg->channels[i] > 64) { fail("rew_end_create: channels must be 32 or 64 per level (got %d)", cfg->channels[i]); return nullptr; }
+  if (cfg->lstm_dim % 4) { fail("rew_end_create: lstm_dim must be a multiple of 4"); return nullptr; }
+  if (init_kernels()) return nullptr;
+  dmd_rew_end* h = new dmd_rew_end();
+  h->cfg = *cfg;
+  dmd_denoiser* core = &h->core;
+  memset(&core->cfg, 0, sizeof(core->cfg));
+  core->cfg.img_channels = cfg->img_channels; core->cfg.num_steps_conditioning = 1; core->cfg.cond_channels = cfg->cond_channels;
+  core->cfg.num_levels = cfg->num_levels; core->cfg.num_actions = cfg->num_actions;
+  for (int i = 0; i < cfg->num_levels; ++i) { core->cfg.depths[i] = cfg->depths[i]; core->cfg.channels[i] = cfg->channels[i]; core->cfg.attn_depths[i] = cfg->attn_depths[i]; }
+  // registration order (rew_end_model.py:27-41, :93-125): encoder.{conv_in, blocks[0..L], downsamples[1..L-1]}, act_emb, lstm, head
+  Walker w{core};
+  core->numel.clear();
+  const int L = cfg->num_levels;
+  const int cin_real = 2 * cfg->img_channels;
+  h->conv_in = w.conv(cfg->channels[0], cin_real, 9, cin_real, round_up(cin_real, 16), 0, 1, false);
+  h->blocks.resize(L + 1);
+  for (int i = 0; i < L; ++i) {
+    const int c1 = cfg->channels[i > 0 ? i - 1 : 0], c2 = cfg->channels[i];
+    for (int k = 0; k < cfg->depths[i]; ++k) h->blocks[i].push_back(w.resblock(k == 0 ? c1 : c2, 0, c2, cfg->attn_depths[i] != 0));
+  }
+  for (int k = 0; k < 2; ++k) h->blocks[L].push_back(w.resblock(cfg->channels[L - 1], 0, cfg->channels[L - 1], true));
+  h->downs.resize(L);
+  for (int i = 1; i < L; ++i) h->downs[i] = w.conv(cfg->channels[i - 1], cfg->channels[i - 1], 9, cfg->channels[i - 1], cfg->channels[i - 1], 0);
+  const int S = cfg->img_size >> (L - 1);
+  h->feat_c = cfg->channels[L - 1]; h->feat_hw = S * S;
+  const long long D = cfg->lstm_dim, K = (long long)h->feat_c * h->feat_hw;
+  h->i_actemb = w.next((long long)cfg->num_actions * cfg->cond_channels);
+  h->i_wih = w.next(4 * D * K); h->i_whh = w.next(4 * D * D); h->i_bih = w.next(4 * D); h->i_bhh = w.next(4 * D);
+  h->i_h0w = w.next(D * D); h->i_h0b = w.next(D); h->i_h2w = w.next(5 * D);
+  core->n_tensors = w.idx;
+  size_t pk = w.pk;
+  core->film_w_off = pk; pk += (size_t)core->film_rows * cfg->cond_channels * 4; pk = (pk + 255) & ~(size_t)255;
+  core->film_b_off = pk; pk += (size_t)core->film_rows * 4; pk = (pk + 255) & ~(size_t)255;
+  core->packed_bytes = pk;
+  return h;
+}
+extern "C" void dmd_rew_end_destroy(dmd_rew_end* h) { delete h; }
+extern "C" int dmd_rew_end_num_tensors(const dmd_rew_end* h) { return h->core.n_tensors; }
+extern "C" size_t dmd_rew_end_packed_bytes(const dmd_rew_end* h) { return h->core.packed_bytes; }
+
+extern "C" int dmd_rew_end_set_weights(dmd_rew_end* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream) {
+  DMD_CHECK(h && ptrs_host && packed, "rew_end set_weights: null argument");
+  dmd_denoiser* core = &h->core;
+  DMD_CHECK(n_ptrs == core->n_tensors, "rew_end set_weights: expected %d tensors (RewEndModel.state_dict order), got %d", core->n_tensors, n_ptrs);
+  cudaStream_t st = (cudaStream_t)stream;
+  core->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
+  core->packed = (uint8_t*)packed;
+  h->planB = 0;
+  if (pack_one(core, h->conv_in, st)) return 1;
+  for (auto& lv : h->blocks) for (auto& r : lv) if (pack_rb(core, r, st)) return 1;
+  for (int i = 1; i < h->cfg.num_levels; ++i) if (pack_one(core, h->downs[i], st)) return 1;
+  return 0;
+}
+
+extern "C" size_t dmd_rew_end_workspace_bytes(dmd_rew_end* h, int rows) {
+  size_t total = 0;
+  h->planB = 0;
+  if (rew_end_layout(h, rows, h->cfg.img_size, h->cfg.img_size, nullptr, &total)) return 0;
+  return total;
+}
+
+// obs / next_obs (b, t, C, S, S) fp32, act (b, t) int64, hx_in / cx_in (b, lstm_dim) or NULL (zeros).
+// Outputs: logits_rew (b, t, 3), logits_end (b, t, 2), hx_out / cx_out (b, lstm_dim).
+extern "C" int dmd_rew_end_predict(dmd_rew_end* h, int b, int t, const float* obs, const float* next_obs, const int64_t* act,
+                                   const float* hx_in, const float* cx_in, float* logits_rew, float* logits_end, float* hx_out,
+                                   float* cx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  DMD_CHECK(h && obs && next_obs && act && logits_rew && logits_end && hx_out && cx_out && workspace, "rew_end predict: null argument");
+  dmd_denoiser* core = &h->core;
+  DMD_CHECK(!core->ptrs.empty() && core->packed, "rew_end predict: call dmd_rew_end_set_weights first");
+  DMD_CHECK(((uintptr_t)workspace & 255) == 0, "rew_end predict: workspace must be 256-byte aligned");
+  const dmd_rew_end_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = b * t, S = c.img_size, HW = S * S, D = c.lstm_dim, CC = c.cond_channels;
+  if (h->planB != rows || h->plan_ws != workspace) {
+    size_t need = 0;
+    h->planB = 0;
+    if (rew_end_layout(h, rows, S, S, nullptr, &need)) return 1;
+    DMD_CHECK(workspace_bytes >= need, "rew_end predict: workspace too small (%zu < %zu)", workspace_bytes, need);
+    if (rew_end_layout(h, rows, S, S, (uint8_t*)workspace, nullptr)) return 1;
+    h->planB = rows; h->plan_ws = workspace;
+  }
+  Plan& pl = core->plan;
+  DMD_CUDA(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st));
+  pack_rew_end_input_kernel<<<dim3((HW + 255) / 256, rows), 256, 0, st>>>(obs, next_obs, act, core->ptrs[h->i_actemb], pl.xin, pl.cond, b, t,
+                                                                          c.img_channels, pl.CP_in, HW, CC, c.num_actions);
+  DMD_LAUNCH_OK();
+  if (linear_launch(pl.cond, (const float*)(core->packed + core->film_w_off), (const float*)(core->packed + core->film_b_off), pl.film,
+                    rows, CC, core->film_rows, 0, st)) return 1;
+  for (const Op& op : pl.ops) {
+    if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
+    else if (op.kind == OP_PREP) { if (prep_launch(op.prep, op.prep_nsrc, st)) return 1; }
+    else { if (attn_launch(op.attn, pl.B, st)) return 1; }
+  }
+  // LSTM over time (torch.nn.LSTM, gate order i f g o), rows of step k are the contiguous block [k*b, (k+1)*b)
+  const int K = h->feat_c * h->feat_hw;
+  const float* hprev = hx_in; const float* cprev = cx_in;
+  if (!hx_in) { DMD_CUDA(cudaMemsetAsync(h->hc[0], 0, (size_t)b * D * 4, st)); hprev = h->hc[0]; }
+  if (!cx_in) { DMD_CUDA(cudaMemsetAsync(h->hc[1], 0, (size_t)b * D * 4, st)); cprev = h->hc[1]; }
+  for (int k = 0; k < t; ++k) {
+    const float* xk = h->feat.data + (size_t)k * b * K;
+    if (linear_launch(xk, core->ptrs[h->i_wih], core->ptrs[h->i_bih], h->x_gates, b, K, 4 * D, 0, st, 0, h->feat_hw)) return 1;
+    if (linear_launch(hprev, core->ptrs[h->i_whh], core->ptrs[h->i_bhh], h->x_gates, b, D, 4 * D, 0, st, 1, 0)) return 1;
+    float* hk = h->y + (size_t)k * b * D;   // y rows of step k (time-major); also the next step's h
+    lstm_gates_kernel<<<(b * D + 255) / 256, 256, 0, st>>>(h->x_gates, cprev, hk, cx_out, b, D);
+    DMD_LAUNCH_OK();
+    hprev = hk; cprev = cx_out;
+  }
+  DMD_CUDA(cudaMemcpyAsync(hx_out, hprev, (size_t)b * D * 4, cudaMemcpyDeviceToDevice, st));
+  // head: Linear(D, D) + SiLU + Linear(D, 5, bias=False) over all (t b) rows
+  if (linear_launch(h->y, core->ptrs[h->i_h0w], core->ptrs[h->i_h0b], h->hid, rows, D, D, 1, st)) return 1;
+  if (linear_launch(h->hid, core->ptrs[h->i_h2w], nullptr, h->logits_tm, rows, D, 5, 0, st)) return 1;
+  split_logits_kernel<<<(rows + 127) / 128, 128, 0, st>>>(h->logits_tm, logits_rew, logits_end, b, t);
   DMD_LAUNCH_OK();
   return 0;
 }

@@ -76,3 +76,25 @@ def allreduce_gradients(params, bucket_bytes: int = 32 << 20, group=None) -> int
         calls += 1
         i = j
     return calls
+
+
+def allreduce_native_gradients(inner_module, group=None) -> int:
+    """Data-parallel gradient averaging for a model whose backward ran natively (diamond_b200 InnerModel): the native
+    backward wrote EVERY parameter gradient into one flat fp32 buffer and autograd adopted views of it as `.grad`, so the whole
+    model is averaged by ONE all_reduce on that buffer (NCCL over NVLink / NVSwitch; the reference wraps each model in DDP,
+    utils.py:105-106, which buckets the same bytes into several collectives).  Falls back to `allreduce_gradients` (flatten,
+    reduce, scatter) when the gradients do not alias the flat buffer (e.g. after gradient accumulation).  Returns the number of
+    collectives issued."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    flat = getattr(inner_module, "last_flat_grad", None)
+    params = [p for p in inner_module.parameters() if p.requires_grad]
+    aliased = flat is not None and all(
+        p.grad is not None and flat.data_ptr() <= p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in params)
+    if not aliased:
+        return allreduce_gradients(params, group=group)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    return 1

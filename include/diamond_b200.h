@@ -286,6 +286,34 @@ int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float* hx_in, co
 int dmd_lambda_returns(const float* rew, const int64_t* end, const int64_t* trunc, const float* val_bootstrap, float* out, int B,
                        int T, double gamma, double lambda_, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reward / termination model: RewEndModel.predict_rew_end (src/models/rew_end_model.py:42-55), called once
+ * per imagined step (src/envs/world_model_env.py:97) and over the burn-in frames of each fresh episode (:120-129).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct dmd_rew_end_config {
+  int lstm_dim;
+  int img_channels;
+  int img_size;
+  int cond_channels;
+  int num_levels;
+  int depths[DMD_MAX_LEVELS];
+  int channels[DMD_MAX_LEVELS];
+  int attn_depths[DMD_MAX_LEVELS];
+  int num_actions;
+} dmd_rew_end_config;
+typedef struct dmd_rew_end dmd_rew_end;
+dmd_rew_end* dmd_rew_end_create(const dmd_rew_end_config* cfg);
+void dmd_rew_end_destroy(dmd_rew_end* h);
+int dmd_rew_end_num_tensors(const dmd_rew_end* h);           /* == len(RewEndModel.state_dict()) */
+size_t dmd_rew_end_packed_bytes(const dmd_rew_end* h);
+int dmd_rew_end_set_weights(dmd_rew_end* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream);
+size_t dmd_rew_end_workspace_bytes(dmd_rew_end* h, int rows);  /* rows = b * t */
+/* obs / next_obs (b, t, C, S, S), act (b, t) int64, hx_in / cx_in (b, lstm_dim) or NULL (zero state).
+ * logits_rew (b, t, 3), logits_end (b, t, 2), hx_out / cx_out (b, lstm_dim). */
+int dmd_rew_end_predict(dmd_rew_end* h, int b, int t, const float* obs, const float* next_obs, const int64_t* act,
+                        const float* hx_in, const float* cx_in, float* logits_rew, float* logits_end, float* hx_out,
+                        float* cx_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
