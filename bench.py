@@ -398,6 +398,72 @@ def train_block(dev, world, rank, batch, steps=5, warmup=2):
             "achieved_tflops_per_gpu": gflop / (tot[1] / steps) / 1e3 * 1e0, "steps": steps, "warmup": warmup}
 
 
+def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1):
+    """cfg 3 of BASELINE.json: one actor-critic update in imagination = `horizon` imagined steps of `envs` environments
+    (native sampler, 3 denoising steps, + native reward/termination model + native policy with autograd nodes), then the loss,
+    BPTT through the rollout, gradient all-reduce when world > 1, clip + AdamW (src/trainer.py:365-378).  Everything on the
+    step path is native; the environment is fed by a synthetic in-memory loader (no dataset on the box)."""
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    from diamond_b200.envs import WorldModelEnv, WorldModelEnvConfig
+    from diamond_b200.models.actor_critic import ActorCritic, ActorCriticConfig, ActorCriticLossConfig
+    from diamond_b200.models.diffusion import Denoiser, DenoiserConfig, DiffusionSamplerConfig, InnerModelConfig
+    from diamond_b200.models.rew_end_model import RewEndModel, RewEndModelConfig
+    from diamond_b200.synthetic import frame_stacks, randomize_module_
+    from diamond_b200.utils import allreduce_gradients
+
+    den = Denoiser(DenoiserConfig(InnerModelConfig(3, 4, 256, [2, 2, 2, 2], [64] * 4, [0] * 4, 4), 0.5, 0.3))
+    randomize_module_(den.inner_model, 2024)
+    rem = RewEndModel(RewEndModelConfig(512, 3, 64, 128, [2, 2, 2, 2], [32] * 4, [0] * 4, 4))
+    randomize_module_(rem, 2025)
+    ac = ActorCritic(ActorCriticConfig(512, 3, 64, [32, 32, 64, 64], [1, 1, 1, 1], 4))
+    randomize_module_(ac, 2026)
+    den, rem, ac = den.to(dev).eval(), rem.to(dev).eval(), ac.to(dev).train()
+
+    class Loader:
+        batch_sampler = types.SimpleNamespace(batch_size=envs)
+
+        def __iter__(self):
+            k = 0
+            while True:
+                obs, act, _ = frame_stacks(envs, 5, 3, 64, 64, 4, 1000 * (rank + 1) + k)
+                k += 1
+                yield types.SimpleNamespace(obs=obs, act=act)
+
+    env = WorldModelEnv(den, rem, Loader(), WorldModelEnvConfig(horizon, 4, DiffusionSamplerConfig(3)))
+    ac.setup_training(env, ActorCriticLossConfig(horizon, 0.985, 0.95, 1.0, 0.001))
+    opt = torch.optim.AdamW(ac.parameters(), lr=1e-4, weight_decay=1e-2, eps=1e-8)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_roll = t_bwd = t_rest = 0.0
+    for it in range(warmup + updates):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        opt.zero_grad(set_to_none=True)
+        loss, logs = ac()
+        e1.record()
+        loss.backward()
+        e2.record()
+        allreduce_gradients(list(ac.parameters()))
+        torch.nn.utils.clip_grad_norm_(ac.parameters(), 100.0)
+        opt.step()
+        e3.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            t_roll += e0.elapsed_time(e1); t_bwd += e1.elapsed_time(e2); t_rest += e2.elapsed_time(e3)
+    tot = max_over_ranks([t_roll + t_bwd + t_rest, t_roll, t_bwd, t_rest], dev)
+    ms = tot[0] / updates
+    return {"workload": "ActorCritic.forward() over WorldModelEnv (%d envs x horizon %d, 3 denoise steps) + backward + clip + AdamW (cfg 3)" % (envs, horizon),
+            "value": envs * horizon * world / (ms * 1e-3), "unit": "imagined frames/s (incl. policy update)", "ms_per_update": ms,
+            "rollout_ms": tot[1] / updates, "backward_ms": tot[2] / updates, "allreduce_clip_adamw_ms": tot[3] / updates,
+            "loss": float(loss), "updates": updates, "warmup": warmup}
+
+
 def wgrad_roofline(dev, batch, peaks):
     """tcgen05 wgrad kernel, 3x3 64->64 at 64x64 over `batch` images (the dominant backward-filter shape), timed alone."""
     import torch
@@ -507,6 +573,12 @@ def run_native(args):
             train = train_block(dev, world, rank, args.train_batch)
         except Exception as e:  # noqa: BLE001
             train = {"error": repr(e)[:300]}
+    imag = None
+    if not args.skip_imagination:
+        try:
+            imag = imagination_block(dev, world, rank, envs=B)
+        except Exception as e:  # noqa: BLE001
+            imag = {"error": repr(e)[:300]}
     if rank == 0:
         peaks, peaks_src = load_peaks()
         roof = conv_roofline(dev, B, peaks, peaks_src)
@@ -540,6 +612,8 @@ def run_native(args):
                 line["train_denoiser"]["wgrad_roofline"] = wgrad_roofline(dev, min(args.train_batch, 64), peaks)
             except Exception as e:  # noqa: BLE001
                 line["train_denoiser"]["wgrad_roofline"] = {"error": repr(e)[:200]}
+        if imag is not None:
+            line["imagination_update"] = imag
         if gpu_base is not None:
             line["gpu_baseline"] = gpu_base
             for k in ("eager", "compiled_reduce_overhead"):
@@ -564,6 +638,7 @@ def main():
     ap.add_argument("--envs", type=int, default=32, help="imagined environments per GPU (config/trainer.yaml actor_critic batch 32)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="development runs: omit the (minutes-long) cpu_baseline leg")
+    ap.add_argument("--skip-imagination", action="store_true", help="omit the imagination + actor-critic update block (cfg 3)")
     ap.add_argument("--skip-train", action="store_true", help="omit the denoiser-training block (cfg 2)")
     ap.add_argument("--train-batch", type=int, default=256, help="denoiser training batch per GPU (config/trainer.yaml: 32; BASELINE cfg 2: 256)")
     ap.add_argument("--skip-gpu-baseline", action="store_true", help="omit the reference-GPU-path leg (eager + torch.compile of the oracle port)")

@@ -138,18 +138,25 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   }
   p->dPW.init(g.PW); p->dPH.init(g.PH);
   p->num_tiles = (g.Q + kTileM - 1) / kTileM;
-  // slab ring: everything that fits next to the resident weights, at most four tiles' worth
+  // slab ring: everything that fits next to the resident weights, at most four tiles' worth.  Two epilogue groups (each with
+  // its own staging tile) when the ring still gets >= 4 slabs and a CTA sees at least two tiles; else one group.
   const int kslabs = (p->Cin + p->Cextra) / 16;
   const uint32_t w_bytes = conv_weight_bytes(p->taps, p->Cin, p->Cextra, p->CoutPad);
-  const ConvSmemLayout L0 = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, 0);
-  const long long budget = 227ll * 1024 - (long long)L0.total;
-  int stages = (int)(budget / (long long)L0.slab_bytes);
+  int groups = tune_int("DMD_CONV_GROUPS", 2) >= 2 ? 2 : 1;
+  int stages = 0;
+  for (;; groups = 1) {
+    const ConvSmemLayout L0 = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, 0, groups);
+    const long long budget = 227ll * 1024 - (long long)L0.total;
+    stages = budget > 0 ? (int)(budget / (long long)L0.slab_bytes) : 0;
+    if (groups == 1 || stages >= (kslabs < 4 ? kslabs + 1 : 4)) break;
+  }
   if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
   { const int cap = tune_int("DMD_CONV_MAX_STAGES", kMaxStages); if (cap >= 2 && stages > cap) stages = cap; }
-  DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d (slab %u B, budget %lld B)", p->W, p->Cin, p->CoutPad, L0.slab_bytes, budget);
+  DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d", p->W, p->Cin, p->CoutPad);
   p->stages = stages;
-  *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages).total;
+  p->egroups = groups;
+  *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages, groups).total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
   return 0;
 }
@@ -170,9 +177,12 @@ static int init_kernels() {
   if (it == states.end()) {
     DevState st;
     DMD_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -200,7 +210,7 @@ static int launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStr
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = tune_int("DMD_NO_PDL", 0) ? 0 : 1;   // bring-up switch: plain stream-ordered launches
   DMD_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
   DMD_LAUNCH_OK();
   return 0;
@@ -210,7 +220,8 @@ template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
-  return launch_pdl(conv_tc_kernel<kCols>, dim3(grid), dim3(kConvThreads), smem, st, p);
+  if (p.egroups == 2) return launch_pdl(conv_tc_kernel<kCols, 2>, dim3(grid), dim3(kConvThreads), smem, st, p);
+  return launch_pdl(conv_tc_kernel<kCols, 1>, dim3(grid), dim3(kConvThreads), smem, st, p);
 }
 
 // ---- prep (GroupNorm / AdaGroupNorm / SiLU / upsample -> PLC16 operand)
@@ -240,6 +251,7 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   }
   p->B = d->B; p->Hs = d->Hs; p->Ws = d->Ws; p->ups = d->upsample;   // 1 nearest-2x, 2 zero insertion (stride-2 adjoint)
   DMD_CHECK(d->upsample >= 0 && d->upsample <= 2, "prep: upsample must be 0, 1 (nearest 2x) or 2 (zero insertion)");
+  DMD_CHECK(d->upsample != 2 || (d->mode == 0 && !d->silu && d->C1 == 0 && !d->dst_raw0 && !d->dst_lo0), "prep: zero insertion is a raw single-source operand");
   p->H = d->upsample ? 2 * d->Hs : d->Hs; p->W = d->upsample ? 2 * d->Ws : d->Ws;
   p->mode = d->mode; p->act = d->silu ? 1 : 0;
   p->film = d->film; p->film_stride = d->film_stride; p->film_off = d->film_off; p->film_ctot = d->C0 + d->C1;
@@ -259,6 +271,10 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   return 0;
 }
 static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
+  if (p.ups == 2) {  // zero insertion: its own kernel (single source, raw mode)
+    const long long total = (long long)p.Qalloc * (p.s[0].Cpad >> 3);
+    return launch_pdl(zero_insert_prep_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
+  }
   return launch_pdl(prep_act_kernel, dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), dim3(kPrepThreads), 0, st, p);
 }
 extern "C" int dmd_prep_plan(const dmd_prep_desc* d, int* blocks, int* pos_per_block, int* sources) {

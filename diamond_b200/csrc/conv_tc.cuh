@@ -89,6 +89,7 @@ struct ConvParams {
   unsigned long long plane_bytes;  // bytes of one chunk plane (same geometry for both sources)
   int P, Palloc;        // halo positions, odd allocation pitch
   int num_tiles, stages;
+  int egroups;          // epilogue groups: 1 = eight warps share every tile; 2 = two groups of four warps take alternate tiles
   FastDiv dPW, dPH;
   int dbg;
   long long* dbg_buf;   // bring-up: clock64 timeline of CTA 0, [role 3][tile 16][event 16]
@@ -102,14 +103,14 @@ struct ConvSmemLayout {
 __host__ __device__ inline uint32_t conv_weight_bytes(int taps, int Cin, int Cextra, int CoutPad) {
   return (((uint32_t)taps * Cin * CoutPad * 2 + 127u) & ~127u) + (uint32_t)Cextra * CoutPad * 2;
 }
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int CoutPad, int Palloc, int stages) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int CoutPad, int Palloc, int stages, int groups = 1) {
   ConvSmemLayout L;
   L.bias_off = 512;
-  L.rowinfo_off = L.bias_off + 128 * 4;              // [128] int2 (out pixel or -1, stat slot)
-  L.sstat_off = L.rowinfo_off + kTileM * 8;          // [epilogue warp 8][slot 3][group 4][2] floats
+  L.rowinfo_off = L.bias_off + 128 * 4;              // [groups][128] int2 (out pixel or -1, stat slot)
+  L.sstat_off = L.rowinfo_off + (uint32_t)groups * kTileM * 8;   // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
   L.stage_off = (L.sstat_off + kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
-  L.w_off = (L.stage_off + kTileM * L.stage_pitch + 127u) & ~127u;
+  L.w_off = (L.stage_off + (uint32_t)groups * kTileM * L.stage_pitch + 127u) & ~127u;   // one staging tile per group
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
   L.slab_bytes = 2u * Palloc * 16;
   L.total = L.a_off + (uint32_t)stages * L.slab_bytes + 16;
@@ -131,7 +132,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #define DMD_TS(role, it_, ev) do { } while (0)
 #endif
 
-template <int kAccCols>  // TMEM columns per accumulator (>= CoutPad); two accumulators are allocated
+// kAccCols: TMEM columns per accumulator (>= CoutPad); two accumulators are allocated.
+// kGroups : epilogue organisation.  1: the eight epilogue warps work on one tile at a time.  2: two independent groups of four
+//           warps (each covers the four TMEM lane quarters) own accumulator 0 / 1 and take alternate tiles, with their own
+//           staging tile and named barriers -- the epilogue is latency-bound (0.84 IPC per SM in the round-1 profile), so two
+//           tiles in flight hide each other's TMEM / shared-memory / barrier latencies.
+template <int kAccCols, int kGroups>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);
@@ -140,11 +146,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   uint64_t* tfull = empty + kMaxStages;      // [2]
   uint64_t* tempty = tfull + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const ConvSmemLayout L = conv_smem_layout(conv_weight_bytes(p.taps, p.Cin, p.Cextra, p.CoutPad), p.CoutPad, p.Palloc, p.stages);
+  const ConvSmemLayout L = conv_smem_layout(conv_weight_bytes(p.taps, p.Cin, p.Cextra, p.CoutPad), p.CoutPad, p.Palloc, p.stages, kGroups);
   float* sbias = reinterpret_cast<float*>(smem + L.bias_off);
-  int2* rowinfo = reinterpret_cast<int2*>(smem + L.rowinfo_off);
-  float* sstat = reinterpret_cast<float*>(smem + L.sstat_off);
-  uint8_t* sStage = smem + L.stage_off;
   uint8_t* sW = smem + L.w_off;
   uint8_t* sA = smem + L.a_off;
 
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps / kGroups); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     const uint32_t extra_bytes = (uint32_t)p.Cextra * p.CoutPad * 2;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_slot);
   for (int i = tid; i < 128; i += blockDim.x)
     sbias[i] = ((p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f) + ((p.bias_extra != nullptr && i < p.Cout) ? __ldg(p.bias_extra + i) : 0.f);
-  for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) reinterpret_cast<float*>(smem + L.sstat_off)[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -289,18 +292,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     __syncwarp();
   } else {
     // =========================================================================================== EPILOGUE (8 warps)
-    const int et = tid - 64;                   // 0..255
-    const int ew = et >> 5;                    // 0..7
+    constexpr int GT = kEpiThreads / kGroups;  // threads per epilogue group
+    constexpr int GW = kEpiWarps / kGroups;    // warps per group (8 or 4): GW / 4 warps share one TMEM lane quarter
+    const int et_all = tid - 64;               // 0..255
+    const int grp = et_all / GT;               // epilogue group of this thread
+    const int et = et_all - grp * GT;          // thread index inside the group
+    const int ew = et >> 5;                    // warp inside the group
+    const int bar0 = 8 + grp * 4;              // named barriers of this group: bar0 .. bar0+3
+    int2* rowinfo = reinterpret_cast<int2*>(smem + L.rowinfo_off) + grp * kTileM;
+    float* sstat = reinterpret_cast<float*>(smem + L.sstat_off) + grp * GW * kStatSlots * kMaxOutGroups * 2;
+    uint8_t* sStage = smem + L.stage_off + (size_t)grp * kTileM * L.stage_pitch;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int first_of_quarter = (ew < 4) ? 1 : 0;   // epilogue warps ew and ew+4 share (warp & 3): they split the columns
     const int nchunks = p.CoutPad >> 4;
-    const int ch_half = (nchunks + 1) >> 1;
-    const int ch_begin = first_of_quarter ? 0 : ch_half, ch_end = first_of_quarter ? ch_half : nchunks;
+    constexpr int kShare = GW / 4;             // warps of the group per quarter: they split the columns
+    const int ch_per = (nchunks + kShare - 1) / kShare;
+    const int ch_begin = (ew >> 2) * ch_per, ch_end = min(nchunks, ch_begin + ch_per);
     const int G = p.ostats ? p.Cout / p.ogs : 1;
     const int L4 = p.Cout >> 2;                // float4 per output row (vector path)
     const bool vec_ok = (p.Cout & 3) == 0 && (L4 & (L4 - 1)) == 0 && L4 <= 32;  // 16/32/64/128 channels
     const int lg = 31 - __clz(L4 > 0 ? L4 : 1);
-    const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = kEpiThreads >> lg;
+    const int c4 = et & (L4 - 1), r0 = et >> lg, rstep = GT >> lg;
     const int ogrp = p.ostats ? (c4 * 4) / p.ogs : 0;   // a thread's channel quad, hence its group, is fixed
     const int lanes_per_group = p.ogs >> 2;            // lanes (float4s) covering one group inside a row
     // GroupNorm partial sums (scalars: arrays indexed by the image slot end up in local memory).  A CTA owns a contiguous
@@ -334,22 +345,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           *reinterpret_cast<float2*>(dstp + 2 * kMaxOutGroups * 2) = make_float2(s2, ss2);
         }
       }
-      named_bar_sync(11, kEpiThreads);   // every reuse of sstat is separated from these reads by barrier 8 or 9
+      named_bar_sync(bar0 + 3, GT);   // every reuse of sstat is separated from these reads by barrier bar0 or bar0+1
       if (et < (multi ? kStatSlots : 1) * G * 2) {
         const int k = et / (G * 2), r = et - k * (G * 2);
         const int og = r >> 1, which = r & 1;
-        float pw[kEpiWarps];
+        float pw[GW];
 #pragma unroll
-        for (int w = 0; w < kEpiWarps; ++w) pw[w] = sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + og) * 2 + which];
-        // fixed-order pairwise tree: deterministic within the CTA
-        const double val = (double)(((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7])));
+        for (int w = 0; w < GW; ++w) pw[w] = sstat[(((size_t)w * kStatSlots + k) * kMaxOutGroups + og) * 2 + which];
+        // fixed-order pairwise tree: deterministic within the group
+        float tsum = (pw[0] + pw[1]) + (pw[2] + pw[3]);
+        if (GW == 8) tsum += (pw[4 % GW] + pw[5 % GW]) + (pw[6 % GW] + pw[7 % GW]);
+        const double val = (double)tsum;
         const int img = img0 + k;
         if (val != 0.0 && img < p.B) atomicAdd(p.ostats + ((size_t)img * G + og) * 2 + which, val);
       }
       s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
     };
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = it & 1;
+    for (int it = grp; it < my_tiles; it += kGroups) {
+      const int b = it & 1;                    // kGroups == 2: accumulator b belongs to group b
       const int q0 = (tile_begin + it) * kTileM;
       const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
       const int q_last = min(q0 + kTileM, p.Q) - 1;
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       float4 rpre[8];
       const bool prefetch = vec_ok && p.resid != nullptr && iters <= 8;
       if (prefetch) {
-        named_bar_sync(10, kEpiThreads);  // rowinfo visible
+        named_bar_sync(bar0 + 2, GT);  // rowinfo visible
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           rpre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + b);   // TMEM accumulator may be overwritten
-      named_bar_sync(8, kEpiThreads);
+      named_bar_sync(bar0, GT);
       if (et == 0) DMD_TS(2, it, 2);
       // ---- pass 2: staging -> (+residual) -> coalesced global stores, GroupNorm partial sums
       if (vec_ok) {
@@ -463,7 +476,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       } else {
         // narrow outputs (conv_out: 3 channels): scalar stores, no statistics
         const int total = kTileM * p.Cout;
-        for (int idx = et; idx < total; idx += kEpiThreads) {
+        for (int idx = et; idx < total; idx += GT) {
           const int row = idx / p.Cout, c = idx - row * p.Cout;
           const int2 ri = rowinfo[row];
           if (ri.x >= 0) {
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         }
       }
       if (et == 0) DMD_TS(2, it, 5);
-      named_bar_sync(9, kEpiThreads);   // staging / rowinfo may be reused; sstat complete
+      named_bar_sync(bar0 + 1, GT);   // staging / rowinfo may be reused; sstat complete
       if (et == 0) DMD_TS(2, it, 6);
       if (et == 0) DMD_TS(2, it, 3);
     }
@@ -576,8 +589,7 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
       if (pl + u * pstep < p.pos_per_block && pa < p.Qalloc) {
         meta[u] = -1;
         off[u] = (size_t)j * p.plane_bytes + (size_t)pa * 16;
-        // ups == 2: zero insertion (adjoint of the stride-2 subsample, blocks.py:96): only even (y, x) carry data
-        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B && (p.ups != 2 || ((x | y) & 1) == 0)) {
+        if (has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
           const int ys = p.ups ? (y >> 1) : y, xs = p.ups ? (x >> 1) : x;
           const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + ys) * p.Ws + xs) * S.C + j * 8);
           v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
@@ -677,6 +689,36 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
     if (pl >= p.pos_per_block) break;
     load_batch();
   }
+}
+
+// Zero-insertion operand (ups == 2): the adjoint of the stride-2 subsample of Downsample (blocks.py:96).  src is the NHWC
+// fp32 gradient at the conv OUTPUT size [B][Hs][Ws][C]; the PLC16 operand at the conv INPUT size (2Hs x 2Ws) carries it at the
+// even (y, x) and zeros everywhere else.  One thread per (position, 8-channel chunk).  (A separate kernel on purpose: adding
+// this case to prep_act_kernel's load predicate made ptxas 12.9 emit a kernel whose coefficient phase went stale.)
+__global__ void __launch_bounds__(256) zero_insert_prep_kernel(const PrepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const PrepSrc& S = p.s[0];
+  const int nch = S.Cpad >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.Qalloc * nch;
+  if (idx >= total) return;
+  const int j = (int)(idx % nch);
+  const int pa = (int)(idx / nch);
+  uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+  const int q = pa - p.G;
+  if (q >= 0 && q < p.Q && j * 8 < S.C) {
+    const uint32_t R = p.dPW.div((uint32_t)q);
+    const int x = q - (int)R * p.PW;
+    const int n = (int)p.dPH.div(R);
+    const int y = (int)R - n * p.PH;
+    if (x < p.W && y < p.H && ((x | y) & 1) == 0) {
+      const float4* gp = reinterpret_cast<const float4*>(S.src + (((size_t)n * p.Hs + (y >> 1)) * p.Ws + (x >> 1)) * S.C + j * 8);
+      const float4 a = __ldg(gp), b = __ldg(gp + 1);
+      packed.x = pack_h2(a.x, a.y); packed.y = pack_h2(a.z, a.w); packed.z = pack_h2(b.x, b.y); packed.w = pack_h2(b.z, b.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(S.dst + (size_t)j * p.plane_bytes + (size_t)pa * 16) = packed;
 }
 
 }  // namespace dmd

@@ -36,11 +36,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a launch error (trap), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch error (trap), never as a hung GPU.  A failed try_wait suspends for
+// an implementation-defined time up to the 1 ms hint (observed: microseconds), so 2^20 failures is seconds to minutes on
+// one phase -- orders of magnitude beyond the longest legitimate wait of any kernel here.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) asm volatile("trap;");
+    if (++spins > (1u << 20)) asm volatile("trap;");
   }
 }
 
