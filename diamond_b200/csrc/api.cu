@@ -142,13 +142,15 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   // its own staging tile) when the ring still gets >= 4 slabs and a CTA sees at least two tiles; else one group.
   const int kslabs = (p->Cin + p->Cextra) / 16;
   const uint32_t w_bytes = conv_weight_bytes(p->taps, p->Cin, p->Cextra, p->CoutPad);
-  int groups = tune_int("DMD_CONV_GROUPS", 2) >= 2 ? 2 : 1;
+  // epilogue organisation: direct (0) unless switched off (DMD_CONV_EPI=0) or a warp's columns would span several GroupNorm groups
+  const bool direct = tune_int("DMD_CONV_EPI", 1) != 0 && (!d->out_stats || d->CoutPad <= 64);
+  int groups = direct ? 0 : (tune_int("DMD_CONV_GROUPS", 2) >= 2 ? 2 : 1);
   int stages = 0;
   for (;; groups = 1) {
     const ConvSmemLayout L0 = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, 0, groups);
     const long long budget = 227ll * 1024 - (long long)L0.total;
     stages = budget > 0 ? (int)(budget / (long long)L0.slab_bytes) : 0;
-    if (groups == 1 || stages >= (kslabs < 4 ? kslabs + 1 : 4)) break;
+    if (groups <= 1 || stages >= (kslabs < 4 ? kslabs + 1 : 4)) break;
   }
   if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -177,6 +179,9 @@ static int init_kernels() {
   if (it == states.end()) {
     DevState st;
     DMD_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -220,6 +225,7 @@ template <int kCols>
 static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
+  if (p.egroups == 0) return launch_pdl(conv_tc_kernel<kCols, 0>, dim3(grid), dim3(kConvThreads), smem, st, p);
   if (p.egroups == 2) return launch_pdl(conv_tc_kernel<kCols, 2>, dim3(grid), dim3(kConvThreads), smem, st, p);
   return launch_pdl(conv_tc_kernel<kCols, 1>, dim3(grid), dim3(kConvThreads), smem, st, p);
 }
@@ -403,8 +409,9 @@ extern "C" int dmd_pack_conv_weight_dgrad(const float* w, void* wpk, int CoutF, 
 extern "C" int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
                                     int c0_real, int c0_store, int precise, void* stream) {
   DMD_CHECK(w && wpk, "pack: null pointer");
-  const int total = taps * Cin * CoutPad * (precise ? 3 : 1);
-  pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store, precise ? 1 : 0);
+  DMD_CHECK(precise >= 0 && precise <= 2, "pack: precise must be 0, 1 (split [W_hi | W_hi | W_lo]) or 2 (low parts only)");
+  const int total = taps * Cin * CoutPad * (precise == 1 ? 3 : 1);
+  pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store, precise);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -476,7 +483,9 @@ struct ConvW {          // one nn.Conv2d
   int w_idx, b_idx;     // indices into the state_dict pointer list
   int Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store;
   int precise = 0;      // split-fp16: K = 3 * Cin
+  int three_pass = 0;   // split-fp16 as three launches (A_hi W_hi, A_lo W_hi, A_hi W_lo) when 3 * Cin weights exceed shared memory
   size_t pk_off;        // byte offset into the packed-weight buffer
+  size_t pk_lo_off = 0; // three_pass: the low-part pack
   // backward-data packs (transposed, tap-flipped; one per source of a channel concat), training only
   int nsrcT = 0; int srcC[2] = {0, 0}; int srcOff[2] = {0, 0}; size_t pkT_off[2] = {0, 0};
 };
@@ -1440,9 +1449,8 @@ int sampler_body(dmd_denoiser* h, const dmd_sampler_config* sc, const SamplerIO&
   SigmaList sl; int K = 0; bool hoist = true;
   for (int i = 0; i + 1 < n && hoist; ++i) {
     const float sigma = sc->sigmas_host[i], next_sigma = sc->sigmas_host[i + 1];
-    const double gamma = (sc->s_tmin <= sigma && sigma <= sc->s_tmax) ? gamma_ : 0.0;
     if (K + 2 > kMaxSamplerEvals) { hoist = false; break; }
-    sl.v[K++] = sigma * (float)(gamma + 1.0);
+    sl.v[K++] = sigma;   // the network is conditioned on sigma, NOT sigma_hat (diffusion_sampler.py:44)
     if (!(sc->order == 1 || next_sigma == 0.0f)) sl.v[K++] = next_sigma;
   }
   float* sig_dev = pl.cs + (size_t)pl.B * 4;  // spare slot after cs: the un-hoisted fallback's scalar sigma
@@ -1479,7 +1487,7 @@ int sampler_body(dmd_denoiser* h, const dmd_sampler_config* sc, const SamplerIO&
       DMD_LAUNCH_OK();
       x = pl.s_xc;
     }
-    if (forward(x, sigma_hat)) return 1;
+    if (forward(x, sigma)) return 1;
     const float dt = next_sigma - sigma_hat;
     if (sc->order == 1 || next_sigma == 0.0f) {
       if (run_wrap(h, pl, x, nullptr, nullptr, xn, nullptr, nullptr, nullptr, 1, sigma_hat, dt, st)) return 1;
@@ -1585,12 +1593,20 @@ struct dmd_actor_critic {
 
 namespace {
 
+// Forward convs of the actor-critic encoder run in split-fp16 (error ~2^-22): MaxPool2d (actor_critic.py:109) turns a 2^-11
+// operand rounding into a different arg-max in a few windows, which moves the encoder GRADIENTS by several per cent against
+// the fp32 reference (measured: 2.6e-2 whole-gradient error with fp16 operands, 1.8e-4 with an exact forward).  The encoder
+// is 0.12 GFLOP, so the 3x tensor work is noise.  K = 3 * Cin per tap when that fits in shared memory, else three launches.
 ConvW ac_conv(dmd_actor_critic* h, int& idx, size_t& pk, int cout, int cin_real, int taps, int c0_store, bool dgrad) {
   ConvW c; c.w_idx = idx++; c.b_idx = idx++;
   h->numel.push_back((long long)cout * cin_real * taps); h->numel.push_back(cout);
   c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
   c.c0_real = cin_real; c.c0_store = c0_store; c.Cin = round_up(c0_store, 16);
-  c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2; pk = (pk + 255) & ~(size_t)255;
+  const size_t w1 = (size_t)taps * c.Cin * c.CoutPad * 2;
+  c.precise = (3 * w1 <= 120 * 1024) ? 1 : 0;
+  c.three_pass = c.precise ? 0 : 1;
+  c.pk_off = pk; pk += w1 * (c.precise ? 3 : 1); pk = (pk + 255) & ~(size_t)255;
+  if (c.three_pass) { c.pk_lo_off = pk; pk += w1; pk = (pk + 255) & ~(size_t)255; }
   if (dgrad) {
     c.nsrcT = 1; c.srcC[0] = cin_real; c.srcOff[0] = 0; c.pkT_off[0] = pk;
     pk += (size_t)taps * round_up(cout, 16) * round_up(cin_real, 16) * 2; pk = (pk + 255) & ~(size_t)255;
@@ -1599,7 +1615,7 @@ ConvW ac_conv(dmd_actor_critic* h, int& idx, size_t& pk, int cout, int cin_real,
 }
 
 struct AcBuffers {
-  float* x0; void* opnd; std::vector<float*> r, y, pooled; std::vector<double*> st_in, st_y; float *gates, *hx, *cx; double* stats; size_t stats_bytes; size_t total;
+  float* x0; void* opnd; void* opnd_lo; std::vector<float*> r, y, pooled; std::vector<double*> st_in, st_y; float *gates, *hx, *cx; double* stats; size_t stats_bytes; size_t total;
 };
 
 // lays out the workspace; base may be null (size query)
@@ -1618,6 +1634,7 @@ int ac_layout(const dmd_actor_critic* h, int B, uint8_t* base, AcBuffers* o) {
   Bump bb{base ? base + o->stats_bytes : nullptr};
   o->x0 = (float*)bb.take((size_t)B * S * S * h->conv0.c0_store * 4);
   o->opnd = bb.take(plc16_bytes(B, S, S, 64));  // one operand buffer: every conv's prep immediately precedes it on the stream
+  o->opnd_lo = bb.take(plc16_bytes(B, S, S, 64));  // its fp16 low part (split-fp16 forward)
   float* cur = (float*)bb.take((size_t)B * S * S * c.channels[0] * 4);  // conv0 output
   o->r.assign(nl, nullptr); o->y.assign(nl, nullptr); o->pooled.assign(nl + 1, nullptr);
   o->pooled[0] = cur;
@@ -1681,7 +1698,8 @@ extern "C" int dmd_actor_critic_set_weights(dmd_actor_critic* h, const float* co
   h->ptrs.assign(ptrs_host, ptrs_host + n_ptrs);
   h->packed = (uint8_t*)packed;
   auto pack = [&](const ConvW& c) {
-    if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, 0, stream)) return 1;
+    if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.precise, stream)) return 1;
+    if (c.three_pass && dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_lo_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, 2, stream)) return 1;
     for (int k = 0; k < c.nsrcT; ++k)
       if (dmd_pack_conv_weight_dgrad(h->ptrs[c.w_idx], h->packed + c.pkT_off[k], c.Cout, c.CinReal, c.srcOff[k], c.srcC[k], c.taps, stream)) return 1;
     return 0;
@@ -1709,22 +1727,31 @@ extern "C" int dmd_actor_critic_forward(dmd_actor_critic* h, int B, const float*
   int S = c.img_size;
   if (dmd_nchw_to_nhwc(obs, b.x0, B, c.img_channels, h->conv0.c0_store, S * S, st)) return 1;
   uint8_t* opnd = (uint8_t*)b.opnd;
+  uint8_t* opnd_lo = (uint8_t*)b.opnd_lo;
   auto run_conv = [&](const ConvW& cw, const float* src, int Csrc, int hw, int pro, int gamma_idx, int beta_idx, const double* st_in,
                       const float* resid, float* out, double* st_out) -> int {
     dmd_prep_desc pd; memset(&pd, 0, sizeof(pd));
     pd.src0 = src; pd.C0 = Csrc; pd.B = B; pd.Hs = hw; pd.Ws = hw; pd.mode = pro; pd.silu = pro ? 1 : 0;
     pd.stats0 = st_in; pd.gs0 = pro ? gn_group_size(Csrc) : 0;
     if (pro) { pd.gamma = h->ptrs[gamma_idx]; pd.beta = h->ptrs[beta_idx]; }
-    pd.eps = kGnEps; pd.dst0 = opnd;
+    pd.eps = kGnEps; pd.dst0 = opnd; pd.dst_lo0 = opnd_lo;   // hi + lo parts: the forward is split-fp16 (see ac_conv)
     PrepParams pp; int nsrc;
     if (prep_fill(&pd, &pp, &nsrc) || prep_launch(pp, nsrc, st)) return 1;
-    dmd_conv_desc d; memset(&d, 0, sizeof(d));
-    d.src0 = opnd; d.C0 = round_up(Csrc, 16); d.B = B; d.H = hw; d.W = hw; d.taps = cw.taps; d.stride = 1;
-    d.wpk = h->packed + cw.pk_off; d.bias = h->ptrs[cw.b_idx]; d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
-    d.residual = resid; d.out = out; d.out_stats = st_out; d.out_gs = gn_group_size(cw.Cout);
-    ConvParams p; size_t smem; int cols;
-    if (conv_fill(&d, &p, &smem, &cols)) return 1;
-    return conv_launch(p, smem, cols, st);
+    // passes: one launch with K = 3*Cin, or (A_hi W_hi) then (A_lo W_hi) and (A_hi W_lo) accumulated in place through `residual`
+    const int npass = cw.three_pass ? 3 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+      dmd_conv_desc d; memset(&d, 0, sizeof(d));
+      d.src0 = (pass == 1) ? opnd_lo : opnd; d.C0 = round_up(Csrc, 16); d.B = B; d.H = hw; d.W = hw; d.taps = cw.taps; d.stride = 1;
+      if (cw.precise) { d.precise = 1; d.src0_lo = opnd_lo; }
+      d.wpk = h->packed + (pass == 2 ? cw.pk_lo_off : cw.pk_off); d.bias = pass == 0 ? h->ptrs[cw.b_idx] : nullptr;
+      d.Cout = cw.Cout; d.CoutPad = cw.CoutPad;
+      d.residual = pass == 0 ? resid : out; d.out = out;
+      d.out_stats = pass == npass - 1 ? st_out : nullptr; d.out_gs = gn_group_size(cw.Cout);
+      ConvParams p; size_t smem; int cols;
+      if (conv_fill(&d, &p, &smem, &cols)) return 1;
+      if (conv_launch(p, smem, cols, st)) return 1;
+    }
+    return 0;
   };
   // conv0 feeds the first GroupNorm -> statistics in its epilogue
   if (run_conv(h->conv0, b.x0, h->conv0.c0_store, S, 0, 0, 0, nullptr, nullptr, b.pooled[0], b.st_in[0])) return 1;

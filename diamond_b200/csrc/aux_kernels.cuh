@@ -412,7 +412,9 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
                                         int CinReal, int Cin, int taps, int c0_real, int c0_store, int precise) {
   // precise: K = 3*Cin laid out as [W_hi | W_hi | W_lo] to meet operands [A_hi | A_lo | A_hi] (split-fp16 product
   // A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo, error ~2^-22 instead of 2^-11)
-  const int K = precise ? 3 * Cin : Cin;
+  // precise == 2: the LOW parts alone, K = Cin (third pass of a three-launch split-fp16 conv whose 3*Cin weights would not fit
+  // in shared memory)
+  const int K = precise == 1 ? 3 * Cin : Cin;
   const int total = taps * K * CoutPad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
@@ -427,7 +429,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
     float v = 0.f;
     if (co < Cout && cr >= 0 && cr < CinReal) v = w[((size_t)co * CinReal + cr) * taps + t];
     const __half hi = __float2half_rn(v);
-    wpk[i] = (seg < 2) ? hi : __float2half_rn(v - __half2float(hi));
+    wpk[i] = (precise != 2 && seg < 2) ? hi : __float2half_rn(v - __half2float(hi));
   }
 }
 

@@ -27,6 +27,7 @@
 // Weights (fp16, [tap][Cin/8][CoutPad][8]) are bulk-copied into shared memory once per CTA and stay resident.
 // TMEM holds two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace dmd {
@@ -103,13 +104,14 @@ struct ConvSmemLayout {
 __host__ __device__ inline uint32_t conv_weight_bytes(int taps, int Cin, int Cextra, int CoutPad) {
   return (((uint32_t)taps * Cin * CoutPad * 2 + 127u) & ~127u) + (uint32_t)Cextra * CoutPad * 2;
 }
+// groups == 0: direct epilogue (registers -> global), no staging tile, row table or statistics scratch
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int CoutPad, int Palloc, int stages, int groups = 1) {
   ConvSmemLayout L;
   L.bias_off = 512;
   L.rowinfo_off = L.bias_off + 128 * 4;              // [groups][128] int2 (out pixel or -1, stat slot)
   L.sstat_off = L.rowinfo_off + (uint32_t)groups * kTileM * 8;   // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
-  L.stage_off = (L.sstat_off + kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 + 127u) & ~127u;
+  L.stage_off = (L.sstat_off + (groups ? kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 : 0) + 127u) & ~127u;
   L.w_off = (L.stage_off + (uint32_t)groups * kTileM * L.stage_pitch + 127u) & ~127u;   // one staging tile per group
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
   L.slab_bytes = 2u * Palloc * 16;
@@ -133,7 +135,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #endif
 
 // kAccCols: TMEM columns per accumulator (>= CoutPad); two accumulators are allocated.
-// kGroups : epilogue organisation.  1: the eight epilogue warps work on one tile at a time.  2: two independent groups of four
+// kGroups : epilogue organisation.  0: DIRECT -- the eight warps read the accumulator with the 16-lane x 256-bit TMEM pattern, whose
+//           register layout puts 32 contiguous bytes of an output row into four neighbouring threads, and store (+bias, +residual)
+//           straight to global memory as full 32-byte sectors: no shared-memory staging, no row table, no named barriers; the
+//           GroupNorm partial sums are reduced with warp shuffles.  The tile loop is bound by the shared-memory port (operand
+//           re-reads of the nine taps), so taking the epilogue's 64 KB per tile off that port is what this buys.
+//           1: the eight epilogue warps work on one tile at a time through a staging tile.  2: two independent groups of four
 //           warps (each covers the four TMEM lane quarters) own accumulator 0 / 1 and take alternate tiles, with their own
 //           staging tile and named barriers -- the epilogue is latency-bound (0.84 IPC per SM in the round-1 profile), so two
 //           tiles in flight hide each other's TMEM / shared-memory / barrier latencies.
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps / kGroups); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kGroups == 0 ? kEpiWarps : kEpiWarps / (kGroups ? kGroups : 1)); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     const uint32_t extra_bytes = (uint32_t)p.Cextra * p.CoutPad * 2;
@@ -180,7 +187,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_slot);
   for (int i = tid; i < 128; i += blockDim.x)
     sbias[i] = ((p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f) + ((p.bias_extra != nullptr && i < p.Cout) ? __ldg(p.bias_extra + i) : 0.f);
-  for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) reinterpret_cast<float*>(smem + L.sstat_off)[i] = 0.f;
+  if (kGroups != 0)
+    for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) reinterpret_cast<float*>(smem + L.sstat_off)[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -292,8 +300,147 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     __syncwarp();
   } else {
     // =========================================================================================== EPILOGUE (8 warps)
-    constexpr int GT = kEpiThreads / kGroups;  // threads per epilogue group
-    constexpr int GW = kEpiWarps / kGroups;    // warps per group (8 or 4): GW / 4 warps share one TMEM lane quarter
+    if constexpr (kGroups == 0) {
+      // ---- direct epilogue: TMEM (16 lanes x 256 bit pattern) -> registers -> (+bias, +residual) -> global, statistics by shuffles
+      const int ew = warp - 2;                   // 0..7
+      const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+      const int half = ew >> 2;                  // two warps share a quarter and split the columns
+      const int nblk = p.CoutPad >> 3;           // 8-column blocks of the accumulator
+      const int hb = (nblk + 1) >> 1;
+      const int blk_begin = half ? hb : 0, blk_end = half ? nblk : hb;
+      const int lr = lane >> 2, lc = (lane & 3) * 2;
+      const bool vec2 = (p.Cout & 1) == 0;
+      const int G = p.ostats ? p.Cout / p.ogs : 1;
+      const int my_grp = p.ostats ? min(G - 1, (blk_begin * 8) / p.ogs) : 0;   // host: all columns of a warp lie in ONE group
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss0 = 0.f, ss1 = 0.f, ss2 = 0.f;
+      int n_cur = -1;
+      auto flush_stats = [&](int img0, bool multi) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+          if (multi) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+            ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+            ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
+          }
+        }
+        if (lane == 0) {
+          double* dst = p.ostats + ((size_t)img0 * G + my_grp) * 2;
+          if (img0 < p.B && (s0 != 0.f || ss0 != 0.f)) { atomicAdd(dst, (double)s0); atomicAdd(dst + 1, (double)ss0); }
+          if (multi) {
+            if (img0 + 1 < p.B && (s1 != 0.f || ss1 != 0.f)) { atomicAdd(dst + (size_t)G * 2, (double)s1); atomicAdd(dst + (size_t)G * 2 + 1, (double)ss1); }
+            if (img0 + 2 < p.B && (s2 != 0.f || ss2 != 0.f)) { atomicAdd(dst + (size_t)G * 4, (double)s2); atomicAdd(dst + (size_t)G * 4 + 1, (double)ss2); }
+          }
+        }
+        s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        const int q0 = (tile_begin + it) * kTileM;
+        const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
+        const int q_last = min(q0 + kTileM, p.Q) - 1;
+        const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;
+        if (n_cur >= 0 && (!single_image || n_lo != n_cur)) { flush_stats(n_cur, false); n_cur = -1; }
+        // the four accumulator rows of this thread: j = 2*h + s -> row quarter*32 + 16*h + lane/4 + 8*s
+        int opix[4], slot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + quarter * 32 + (j >> 1) * 16 + lr + (j & 1) * 8;
+          opix[j] = -1; slot[j] = 0;
+          if (q < p.Q) {
+            const uint32_t R = p.dPW.div((uint32_t)q);
+            const int x = q - (int)R * p.PW;
+            const int n = (int)p.dPH.div(R);
+            const int y = (int)R - n * p.PH;
+            bool valid = (x < p.W) && (y < p.H);
+            int yo = y, xo = x, Ho = p.H, Wo = p.W;
+            if (p.stride == 2) {
+              valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
+              yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+            }
+            if (valid) { opix[j] = (n * Ho + yo) * Wo + xo; slot[j] = n - n_lo; }
+          }
+        }
+        bool waited = false;
+        auto chunk = [&](auto nbc, auto vecc, int blk) {
+          constexpr int NB = decltype(nbc)::value;
+          constexpr bool VEC = decltype(vecc)::value;   // even Cout: 8-byte accesses (every layer but conv_out / the 15-channel dgrad)
+          const int col0 = blk * 8 + lc;           // first of this thread's two columns in block 0 of the chunk
+          // residual first: it does not depend on the accumulator, so for the first chunk its latency hides behind the MMAs
+          float2 rr[4][NB];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+              rr[j][k] = make_float2(0.f, 0.f);
+              const int col = col0 + 8 * k;
+              if (p.resid != nullptr && opix[j] >= 0 && col < p.Cout) {
+                const float* rp = p.resid + (size_t)opix[j] * p.Cout + col;
+                if (VEC) rr[j][k] = __ldg(reinterpret_cast<const float2*>(rp));
+                else { rr[j][k].x = __ldg(rp); if (col + 1 < p.Cout) rr[j][k].y = __ldg(rp + 1); }
+              }
+            }
+          if (!waited) {
+            mbar_wait(tfull + b, ((uint32_t)it >> 1) & 1u);
+            tc_fence_after_sync();
+            waited = true;
+          }
+          uint32_t r[8 * NB];
+          const uint32_t ta = tmem_base + (uint32_t)b * kAccCols + (uint32_t)(blk * 8) + ((uint32_t)(quarter * 32) << 16);
+          tmem_ld_16x256b_pair<NB>(ta, ta + (16u << 16), r);
+          if (blk + NB >= blk_end) {               // last chunk of this warp: the accumulator may be overwritten
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + b);
+          }
+          float2 bv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k) bv[k] = (col0 + 8 * k < p.Cout) ? *reinterpret_cast<const float2*>(sbias + col0 + 8 * k) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (opix[j] >= 0) {
+              float* op = p.out + (size_t)opix[j] * p.Cout + col0;
+              float ps = 0.f, pss = 0.f;
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+                if (col0 + 8 * k < p.Cout) {
+                  const int ri = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1);
+                  float2 o;
+                  o.x = __uint_as_float(r[ri]) + bv[k].x + rr[j][k].x;
+                  o.y = __uint_as_float(r[ri + 1]) + bv[k].y + rr[j][k].y;
+                  if (VEC) *reinterpret_cast<float2*>(op + 8 * k) = o;
+                  else { op[8 * k] = o.x; if (col0 + 8 * k + 1 < p.Cout) op[8 * k + 1] = o.y; }
+                  ps += o.x + o.y;
+                  pss = fmaf(o.x, o.x, fmaf(o.y, o.y, pss));
+                }
+              }
+              if (p.ostats != nullptr) {
+                const int sl = single_image ? 0 : slot[j];
+                s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
+                s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
+                s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
+              }
+            }
+          }
+        };
+        for (int blk = blk_begin; blk < blk_end;) {
+          const int rem = blk_end - blk;
+          if (!vec2) { chunk(std::integral_constant<int, 1>{}, std::false_type{}, blk); blk += 1; }   // odd Cout: narrow outputs only
+          else if (rem >= 4) { chunk(std::integral_constant<int, 4>{}, std::true_type{}, blk); blk += 4; }
+          else if (rem >= 2) { chunk(std::integral_constant<int, 2>{}, std::true_type{}, blk); blk += 2; }
+          else { chunk(std::integral_constant<int, 1>{}, std::true_type{}, blk); blk += 1; }
+        }
+        if (p.ostats != nullptr) {
+          if (single_image) n_cur = n_lo;            // keep running across the single-image tiles of this CTA
+          else { flush_stats(n_lo, true); n_cur = -1; }
+        }
+      }
+      if (n_cur >= 0) flush_stats(n_cur, false);
+    } else {
+    constexpr int GT = kEpiThreads / (kGroups ? kGroups : 1);  // threads per epilogue group
+    constexpr int GW = kEpiWarps / (kGroups ? kGroups : 1);    // warps per group (8 or 4): GW / 4 warps share one TMEM lane quarter
     const int et_all = tid - 64;               // 0..255
     const int grp = et_all / GT;               // epilogue group of this thread
     const int et = et_all - grp * GT;          // thread index inside the group
@@ -361,7 +508,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
       s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
     };
-    for (int it = grp; it < my_tiles; it += kGroups) {
+    for (int it = grp; it < my_tiles; it += (kGroups ? kGroups : 1)) {
       const int b = it & 1;                    // kGroups == 2: accumulator b belongs to group b
       const int q0 = (tile_begin + it) * kTileM;
       const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
@@ -493,6 +640,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       if (et == 0) DMD_TS(2, it, 3);
     }
     if (n_cur >= 0) flush_stats(n_cur, false);
+    }  // staged epilogue
   }
   tc_fence_before_sync();
   __syncthreads();

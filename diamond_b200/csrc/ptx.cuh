@@ -141,6 +141,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- TMEM -> registers, 16 lanes x 256 bit pattern (x NB column blocks)
+// One instruction reads 16 TMEM lanes x (8 * NB) fp32 columns.  Thread i of the warp receives, for column block k:
+//   r[4k + 0..1] = (lane0 + i/4    , col0 + 8k + 2*(i%4) + {0,1})
+//   r[4k + 2..3] = (lane0 + i/4 + 8, col0 + 8k + 2*(i%4) + {0,1})
+// i.e. four neighbouring threads hold 32 contiguous bytes of one accumulator row: the registers can go straight to NHWC
+// global memory as full 32-byte sectors, with no shared-memory transpose.  The pair form issues the two 16-lane halves of the
+// warp's 32-lane quarter and waits once (loads + wait in ONE asm statement: the registers cannot be consumed early).
+template <int NB>
+__device__ __forceinline__ void tmem_ld_16x256b_pair(uint32_t taddr_lo, uint32_t taddr_hi, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld_16x256b_pair<1>(uint32_t taddr_lo, uint32_t taddr_hi, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%8];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x1.b32 {%4, %5, %6, %7}, [%9];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr_lo), "r"(taddr_hi)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_16x256b_pair<2>(uint32_t taddr_lo, uint32_t taddr_hi, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_lo), "r"(taddr_hi)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_16x256b_pair<4>(uint32_t taddr_lo, uint32_t taddr_hi, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr_lo), "r"(taddr_hi)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start
 // its prologue now.  wait: block until the previous kernel has completed and its memory is visible.

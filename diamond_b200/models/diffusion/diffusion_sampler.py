@@ -57,6 +57,13 @@ class DiffusionSampler:
                 obs=torch.empty(b, t * c, h, w, device=device), act=torch.empty(b, t, dtype=torch.long, device=device))}
         return self._buf[key]
 
+    def _check_stack(self, t: int, c: int) -> None:
+        # the reference fails inside act_emb / conv_in on a wrong stack depth (inner_model.py:45-46); fail as loudly here
+        icfg = self.denoiser.cfg.inner_model
+        if t != icfg.num_steps_conditioning or c != icfg.img_channels:
+            raise RuntimeError(f"sample: frame stack of {t} x {c} channels, the denoiser is conditioned on "
+                               f"{icfg.num_steps_conditioning} x {icfg.img_channels}")
+
     def _draw_noise(self, buf) -> None:
         """RNG stream parity with the reference: x first (diffusion_sampler.py:36), then one eps per churned step (:42)."""
         traj, eps = buf["traj"], buf["eps"]
@@ -79,6 +86,7 @@ class DiffusionSampler:
     @torch.no_grad()
     def sample(self, prev_obs: Tensor, prev_act: Tensor) -> Tuple[Tensor, List[Tensor]]:  # diffusion_sampler.py:31-58
         b, t, c, h, w = prev_obs.size()
+        self._check_stack(t, c)
         buf = self._buffers(b, t, c, h, w, prev_obs.device)
         buf["obs"].copy_(prev_obs.reshape(b, t * c, h, w))   # stable addresses: the captured graph is replayed as is
         buf["act"].copy_(prev_act)
@@ -93,6 +101,7 @@ class DiffusionSampler:
         logical slot k at physical slot (head + k) % T; the new frame is written straight into `out_frame` (a ring slot).
         Nothing is staged or rolled.  Returns the trajectory buffer (num_sigmas, B, C, H, W), valid until the next call."""
         t, b, c, h, w = frames.size()
+        self._check_stack(t, c)
         buf = self._buffers(b, t, c, h, w, frames.device)
         self._draw_noise(buf)
         self._run(frames, acts, head, buf, out_frame, b, h, w)

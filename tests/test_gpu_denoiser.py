@@ -250,7 +250,8 @@ def test_world_model_env_runs_on_native_sampler():
         def __iter__(self):
             g = torch.Generator().manual_seed(0)
             while True:
-                yield SimpleNamespace(obs=torch.rand(4, 5, 3, 64, 64, generator=g) * 2 - 1, act=torch.randint(0, 4, (4, 5), generator=g))
+                # segments of num_steps_conditioning frames, as the trainer's loader builds them (trainer.py make_data_loader seq_length)
+                yield SimpleNamespace(obs=torch.rand(4, 4, 3, 64, 64, generator=g) * 2 - 1, act=torch.randint(0, 4, (4, 4), generator=g))
 
     env = WorldModelEnv(den, RewEnd(), Loader(), WorldModelEnvConfig(3, 2, DiffusionSamplerConfig(3)))
     cfg = O.DenoiserCfg(inner=inner)

@@ -38,7 +38,7 @@ def test_dominant_conv_plan():
     assert rc == 0
     assert i.tiles == -(-32 * 65 * 65 // 128) == 1057
     assert i.kslabs == 4 and i.tmem_cols == 64
-    assert i.stages == 10      # what fits next to 72 KB of weights + two 34 KB staging tiles (two epilogue groups): 2.5 tiles' worth of 8.2 KB slabs
+    assert i.stages == 16      # direct epilogue (no staging tile): four tiles' worth of 8.2 KB slabs next to 72 KB of weights
     assert i.weight_bytes == 9 * 64 * 64 * 2
     assert i.smem_bytes <= 227 * 1024
 
@@ -87,13 +87,13 @@ def test_conv_rejections_fail_loudly(kw, needle):
 
 
 @pytest.mark.parametrize("kw,w_ok,w_bad", [
-    (dict(), 800, 880),                                          # 64 -> 64: 72 KB of weights
-    (dict(C0=64, C1=64, src1=P), 296, 320),                      # 128 -> 64: 144 KB of weights
-    (dict(Cout=128, CoutPad=128), 32, 64),                       # 64 -> 128: 144 KB of weights + 66 KB of staging
+    (dict(), 1160, 1168),                                        # 64 -> 64: 72 KB of weights
+    (dict(C0=64, C1=64, src1=P), 584, 592),                      # 128 -> 64: 144 KB of weights
+    (dict(Cout=128, CoutPad=128), 584, 592),                     # 64 -> 128: 144 KB of weights
 ])
 def test_width_limit_is_the_shared_memory_ring(kw, w_ok, w_bad):
-    """The halo slab is 32*(128 + 2*(W+2)) bytes and two of them must fit next to the resident weights and the staging
-    tile; wider images are rejected (config-5 shapes need a strip path)."""
+    """The halo slab is 32*(128 + 2*(W+2)) bytes and two of them must fit next to the resident weights (the direct epilogue
+    needs no staging tile); wider images are rejected (config-5 shapes need a strip path)."""
     rc, i, err = _conv(B=1, H=8, W=w_ok, **kw)
     assert rc == 0 and i.stages >= 2, err
     rc, _, err = _conv(B=1, H=8, W=w_bad, **kw)
