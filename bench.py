@@ -395,7 +395,7 @@ def train_block(dev, world, rank, batch, steps=5, warmup=2):
             "value": batch * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "fwd_bwd_ms": tot[1] / steps,
             "allreduce_ms": tot[2] / steps, "clip_adamw_ms": tot[3] / steps, "collectives_per_step": ncoll if world > 1 else 0,
             "allreduce_bytes": int(sum(p.numel() for p in den.parameters()) * 4), "loss": float(loss),
-            "achieved_tflops_per_gpu": gflop / (tot[1] / steps),  # GFLOP / ms = TFLOP/s "steps": steps, "warmup": warmup}
+            "achieved_tflops_per_gpu": gflop / (tot[1] / steps), "steps": steps, "warmup": warmup}
 
 
 def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1):
