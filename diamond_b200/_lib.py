@@ -75,6 +75,9 @@ SIGNATURES = {
     "dmd_version": (_i, []),
     "dmd_last_error": (C.c_char_p, []),
     "dmd_launch_count": (C.c_longlong, [_i]),
+    "dmd_ktrace_begin": (_i, [_i]),
+    "dmd_ktrace_end": (_i, [_vp, _i]),
+    "dmd_ktrace_name": (C.c_char_p, [_i]),
     "dmd_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dmd_plc16_bytes": (_sz, [_i, _i, _i, _i]),
     "dmd_prep_act": (_i, [C.POINTER(PrepDesc), _vp]),

@@ -57,6 +57,38 @@ extern "C" long long dmd_launch_count(int reset) {
   return v;
 }
 
+// ---- kernel trace (diagnostics; scripts/ktrace.py): launches issued between dmd_ktrace_begin and dmd_ktrace_end get one slot
+// each in a device buffer and stamp the GPU nanosecond timer when their inputs are ready
+static long long* g_kt_buf = nullptr;
+static int g_kt_cap = 0, g_kt_n = 0;
+static bool g_kt_on = false;
+static std::vector<std::string> g_kt_names;
+static long long* kt_slot(const char* kind, int grid, int aux) {
+  if (!g_kt_on || g_kt_n >= g_kt_cap) return nullptr;
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%s grid=%d aux=%d", kind, grid, aux);
+  g_kt_names.push_back(buf);
+  return g_kt_buf + g_kt_n++;
+}
+extern "C" int dmd_ktrace_begin(int capacity) {
+  if (g_kt_cap < capacity) {
+    if (g_kt_buf) cudaFree(g_kt_buf);
+    if (cudaMalloc(&g_kt_buf, (size_t)capacity * 8) != cudaSuccess) { g_kt_buf = nullptr; g_kt_cap = 0; g_err = "ktrace: cudaMalloc failed"; return 1; }
+    g_kt_cap = capacity;
+  }
+  cudaMemset(g_kt_buf, 0, (size_t)g_kt_cap * 8);
+  g_kt_n = 0; g_kt_names.clear(); g_kt_on = true;
+  return 0;
+}
+// stops assigning slots; copies the stamps (ns) to `stamps` and returns the number of traced launches (call after a device sync)
+extern "C" int dmd_ktrace_end(long long* stamps, int capacity) {
+  g_kt_on = false;
+  const int n = g_kt_n < capacity ? g_kt_n : capacity;
+  if (n > 0 && stamps) cudaMemcpy(stamps, g_kt_buf, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  return n;
+}
+extern "C" const char* dmd_ktrace_name(int i) { return (i >= 0 && i < (int)g_kt_names.size()) ? g_kt_names[i].c_str() : ""; }
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int gn_group_size(int C) {  // blocks.py:12,27: num_groups = max(1, C // 32)
   int G = C / 32 > 1 ? C / 32 : 1;
@@ -222,9 +254,11 @@ static int launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStr
 }
 
 template <int kCols>
-static int conv_launch_t(const ConvParams& p, size_t smem, cudaStream_t st) {
+static int conv_launch_t(const ConvParams& p0, size_t smem, cudaStream_t st) {
   if (init_kernels()) return 1;
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;  // persistent: one CTA per SM
+  const int grid = p0.num_tiles < g_num_sms ? p0.num_tiles : g_num_sms;  // persistent: one CTA per SM
+  ConvParams p = p0;
+  p.ktrace = kt_slot(p.taps == 9 ? "conv3x3" : "conv1x1", p.num_tiles, (p.Cin + p.Cextra) * 1000 + p.W);
   if (p.egroups == 0) return launch_pdl(conv_tc_kernel<kCols, 0>, dim3(grid), dim3(kConvThreads), smem, st, p);
   if (p.egroups == 2) return launch_pdl(conv_tc_kernel<kCols, 2>, dim3(grid), dim3(kConvThreads), smem, st, p);
   return launch_pdl(conv_tc_kernel<kCols, 1>, dim3(grid), dim3(kConvThreads), smem, st, p);
@@ -276,7 +310,9 @@ static int prep_fill(const dmd_prep_desc* d, PrepParams* p, int* nsrc) {
   *nsrc = d->C1 ? 2 : 1;
   return 0;
 }
-static int prep_launch(const PrepParams& p, int nsrc, cudaStream_t st) {
+static int prep_launch(const PrepParams& p0, int nsrc, cudaStream_t st) {
+  PrepParams p = p0;
+  p.ktrace = kt_slot("prep", (p.Qalloc + p.pos_per_block - 1) / p.pos_per_block * nsrc, p.mode * 1000 + p.W);
   if (p.ups == 2) {  // zero insertion: its own kernel (single source, raw mode)
     const long long total = (long long)p.Qalloc * (p.s[0].Cpad >> 3);
     return launch_pdl(zero_insert_prep_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
@@ -432,8 +468,10 @@ static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
             "attn: unsupported shape L=%d C=%d gs=%d (built for 8x8 = 64 tokens, C in {32, 64})", p.L, p.C, p.gs);
   if (init_kernels()) return 1;
   const size_t smem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * p.C + 4));
-  if (p.C == 64) attn_kernel<64><<<B, kAttnThreads, smem, st>>>(p);
-  else attn_kernel<32><<<B, kAttnThreads, smem, st>>>(p);
+  AttnParams pt = p;
+  pt.ktrace = kt_slot("attn", B, p.C);
+  if (p.C == 64) attn_kernel<64><<<B, kAttnThreads, smem, st>>>(pt);
+  else attn_kernel<32><<<B, kAttnThreads, smem, st>>>(pt);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -1187,7 +1225,7 @@ int run_wrap(dmd_denoiser* h, Plan& pl, const float* x, float* model_out, float*
              const float* d_prev, const float* x0, int mode, float sigma_hat, float dt, cudaStream_t st) {
   const int HW = pl.H * pl.W, total = pl.B * h->cfg.img_channels * HW;
   wrap_update_kernel<<<(total + 255) / 256, 256, 0, st>>>(pl.fout, x, pl.cs, model_out, denoised, x_out, d_out, d_prev, x0,
-                                                         mode, sigma_hat, dt, h->cfg.img_channels, pl.CF, HW, total);
+                                                         mode, sigma_hat, dt, h->cfg.img_channels, pl.CF, HW, total, kt_slot("wrap", (total + 255) / 256, mode));
   DMD_LAUNCH_OK();
   return 0;
 }

@@ -239,6 +239,7 @@ struct AttnParams {
   double* ostats;       // [B][G][2] or null
   int L, C, gs;
   float eps;
+  long long* ktrace = nullptr;
 };
 
 constexpr int kAttnThreads = 512;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnParams p) 
   float* qkv = xs + L * XP;     // [L][QP]   (QP*4 bytes is a multiple of 16: rows are float4-addressable)
   float* ys = qkv + L * QP;     // [L][XP]
   const int n = blockIdx.x, tid = threadIdx.x;
+  if (n == 0 && tid == 0) ktrace_stamp(p.ktrace);
   const int G = C / p.gs;
   const float* xg = p.x + (size_t)n * L * C;
   for (int i = tid; i < L * C; i += kAttnThreads) {
@@ -372,8 +374,9 @@ __global__ void wrap_update_kernel(const float* __restrict__ F, const float* __r
                                    float* __restrict__ model_out_nchw, float* __restrict__ denoised,
                                    float* __restrict__ x_out, float* __restrict__ d_out, const float* __restrict__ d_prev,
                                    const float* __restrict__ x0, int mode, float sigma_hat, float dt, int Cimg, int CF,
-                                   int HW, int total) {
+                                   int HW, int total, long long* ktrace) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // NCHW linear index
+  if (i == 0) ktrace_stamp(ktrace);
   if (i >= total) return;
   const int pix = i % HW, c = (i / HW) % Cimg, n = i / (HW * Cimg);
   const float f = F[((size_t)n * HW + pix) * CF + c];

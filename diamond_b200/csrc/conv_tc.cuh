@@ -94,6 +94,7 @@ struct ConvParams {
   FastDiv dPW, dPH;
   int dbg;
   long long* dbg_buf;   // bring-up: clock64 timeline of CTA 0, [role 3][tile 16][event 16]
+  long long* ktrace;    // diagnostics: globaltimer stamp when the kernel's inputs are ready, or null
 };
 
 struct ConvSmemLayout {
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // operands / residual / statistics come from earlier kernels
+  if (blockIdx.x == 0 && tid == 64) ktrace_stamp(p.ktrace);
 
   if (warp == 0) {
     // =========================================================================================== PRODUCER (TMA)
@@ -679,6 +681,7 @@ struct PrepParams {
   unsigned long long plane_bytes;
   int pos_per_block;
   FastDiv dPW, dPH;
+  long long* ktrace;
 };
 
 constexpr int kPrepThreads = 256;
@@ -703,6 +706,7 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
   __shared__ float smr[2][4][2];                    // (mean, rstd) per (image slot, group)
   pdl_launch_dependents();
   pdl_wait();
+  if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) ktrace_stamp(p.ktrace);
   const PrepSrc& S = p.s[blockIdx.z];
   const int nch = S.Cpad >> 3;
   const int pa0 = blockIdx.x * p.pos_per_block;     // first allocation position of this block

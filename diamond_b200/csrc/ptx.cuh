@@ -201,6 +201,17 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- kernel trace (diagnostics)
+// One thread stores the GPU's nanosecond timer once the kernel's dependencies are satisfied: consecutive stamps of a stream of
+// kernels give the in-graph duration of each (scripts/ktrace.py).  A null pointer (the production setting) costs one test.
+__device__ __forceinline__ void ktrace_stamp(long long* slot) {
+  if (slot != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = (long long)t;
+  }
+}
+
 // ---------------------------------------------------------------- small math
 // SiLU with the bare SFU approximations (5 instructions): v * rcp(1 + 2^(-v*log2 e)).  ex2/rcp.approx.ftz carry ~2 ulp;
 // 1 + e >= 1 so rcp needs no range fix-up (e = +inf -> 0), unlike __fdividef / __expf which add ~4 instructions each.

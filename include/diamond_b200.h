@@ -27,6 +27,14 @@ int dmd_version(void);
 const char* dmd_last_error(void);
 /* Number of kernels launched by this library on the calling thread since the last reset (bench.py gpu_launches). */
 long long dmd_launch_count(int reset);
+/* Diagnostics: in-stream kernel trace.  Between dmd_ktrace_begin(capacity) and dmd_ktrace_end every conv / prep / attention /
+ * wrap launch issued by this library (also into a CUDA graph being captured) gets a slot and stores the GPU nanosecond timer
+ * when its inputs are ready; dmd_ktrace_end (after a device synchronisation) copies the stamps out and returns their count,
+ * dmd_ktrace_name(i) describes launch i.  Differences of consecutive stamps are the in-graph kernel durations
+ * (scripts/ktrace.py).  Not thread-safe; off (null slots, one predicated test per kernel) unless begun. */
+int dmd_ktrace_begin(int capacity);
+int dmd_ktrace_end(long long* stamps, int capacity);
+const char* dmd_ktrace_name(int i);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Per-op entry points (NHWC fp32 activations).
