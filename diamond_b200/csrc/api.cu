@@ -15,6 +15,7 @@
 #include "../../include/diamond_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_tc.cuh"
+#include "conv_fused.cuh"
 #include "wgrad_tc.cuh"
 #include "bwd_kernels.cuh"
 
@@ -220,6 +221,9 @@ static int init_kernels() {
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -345,6 +349,18 @@ static int conv_launch(const ConvParams& p, size_t smem, int tmem_cols, cudaStre
     case 32: return conv_launch_t<32>(p, smem, st);
     case 64: return conv_launch_t<64>(p, smem, st);
     default: return conv_launch_t<128>(p, smem, st);
+  }
+}
+
+static int fused_launch(const FusedParams& f0, size_t smem, int tmem_cols, cudaStream_t st) {
+  if (init_kernels()) return 1;
+  FusedParams f = f0;
+  f.c.ktrace = kt_slot(f.c.taps == 9 ? "fused3x3" : "fused1x1", f.c.num_tiles, (f.c.Cin + f.c.Cextra) * 1000 + f.c.W);
+  const dim3 grid(f.c.num_tiles), block(kConvThreads);
+  switch (tmem_cols) {
+    case 32: return launch_pdl(conv_fused_kernel<32>, grid, block, smem, st, f);
+    case 64: return launch_pdl(conv_fused_kernel<64>, grid, block, smem, st, f);
+    default: return launch_pdl(conv_fused_kernel<128>, grid, block, smem, st, f);
   }
 }
 
@@ -537,12 +553,19 @@ struct ResBlockW {
 
 struct Tens { float* data; double* stats; int C, H, W, gs; float* grad = nullptr; int gid = -1; };
 
-enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2 };
-struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; };
+enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2, OP_FUSED = 3 };
+struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; FusedParams fused; };
 constexpr int kScratchSlots = 10;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
 
 // PLC16 operands produced by one prep launch (op = index of that launch in Plan::ops, replayed by the backward pass)
-struct Operand { uint8_t *n0 = nullptr, *n1 = nullptr, *r0 = nullptr, *r1 = nullptr, *nl0 = nullptr, *rl0 = nullptr, *rl1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0, op = -1; };
+struct Operand {
+  uint8_t *n0 = nullptr, *n1 = nullptr, *r0 = nullptr, *r1 = nullptr, *nl0 = nullptr, *rl0 = nullptr, *rl1 = nullptr; int C0 = 0, C1 = 0, H = 0, W = 0, op = -1;
+  // description of the transform (always filled).  lazy: no prep launch has been emitted -- the consumer either runs the
+  // transform inside its own kernel (conv_fused_kernel, small problems) or materialises the operand first
+  bool lazy = false;
+  Tens a{}, b{}; bool has_b = false;
+  int upsample = 0, mode = 0; const FilmW* film = nullptr; int gamma_idx = 0, beta_idx = 0; bool silu = false, also_raw = false, split = false;
+};
 
 // backward op list (training).  Parameter-gradient destinations are OFFSETS into the caller's flat gradient buffer.
 enum BKind { B_PREP = 0, B_CONV, B_WGRAD, B_COLSUM, B_NORM1, B_NORM2, B_AFFINE, B_POOL, B_ADD, B_ATTN, B_MEMSET, B_SGEMM, B_FILMW,
@@ -757,32 +780,102 @@ struct PlanBuilder {
   // split: also emit the low fp16 part of the operand that a precise conv will read (raw if also_raw, else the main one)
   Operand prep(const Tens& a, const Tens* b, int upsample, int mode, const FilmW* film, int gamma_idx, int beta_idx, bool silu, bool also_raw, bool split = false) {
     Operand o;
+    o.a = a; o.has_b = b != nullptr; if (b) o.b = *b;
+    o.upsample = upsample; o.mode = mode; o.film = film; o.gamma_idx = gamma_idx; o.beta_idx = beta_idx; o.silu = silu; o.also_raw = also_raw; o.split = split;
+    o.C0 = round_up(a.C, 16); o.C1 = b ? round_up(b->C, 16) : 0;
+    o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
+    // small problems (at most one tile per SM): leave the transform to the consuming conv (conv_fused_kernel); never in
+    // training plans, whose backward replays the prep launches
+    const Plc g = plc_geometry(pl->B, o.H, o.W);
+    const int tiles = (g.Q + kTileM - 1) / kTileM;
+    o.lazy = !pl->train && g_num_sms > 0 && tiles <= g_num_sms && tune_int("DMD_FUSE_SMALL", 1) != 0 && upsample != 2 &&
+             a.C % 16 == 0 && (!b || b->C % 16 == 0);
+    if (!o.lazy) materialize(o);
+    return o;
+  }
+  void materialize(Operand& o) {
+    if (!o.lazy && o.n0) return;
+    o.lazy = false;
+    const Tens& a = o.a; const Tens* b = o.has_b ? &o.b : nullptr;
     dmd_prep_desc d; memset(&d, 0, sizeof(d));
     d.src0 = a.data ? a.data : (const float*)1; d.C0 = a.C; d.src1 = b ? (b->data ? b->data : (const float*)1) : nullptr; d.C1 = b ? b->C : 0;
-    d.B = pl->B; d.Hs = a.H; d.Ws = a.W; d.upsample = upsample; d.mode = mode; d.silu = silu;
-    if (mode) {
+    d.B = pl->B; d.Hs = a.H; d.Ws = a.W; d.upsample = o.upsample; d.mode = o.mode; d.silu = o.silu;
+    if (o.mode) {
       d.stats0 = a.stats ? a.stats : (const double*)1; d.gs0 = a.gs;
       if (b) { d.stats1 = b->stats ? b->stats : (const double*)1; d.gs1 = b->gs; }
     }
-    if (mode == 1) { d.film = pl->film ? pl->film : (const float*)1; d.film_stride = h->film_rows; d.film_off = film->off; }
-    if (mode == 2) { d.gamma = P(gamma_idx) ? P(gamma_idx) : (const float*)1; d.beta = P(beta_idx) ? P(beta_idx) : (const float*)1; }
+    if (o.mode == 1) { d.film = pl->film ? pl->film : (const float*)1; d.film_stride = h->film_rows; d.film_off = o.film->off; }
+    if (o.mode == 2) { d.gamma = P(o.gamma_idx) ? P(o.gamma_idx) : (const float*)1; d.beta = P(o.beta_idx) ? P(o.beta_idx) : (const float*)1; }
     d.eps = kGnEps;
     o.n0 = scratch(); d.dst0 = o.n0;
     if (b) { o.n1 = scratch(); d.dst1 = o.n1; }
-    if (also_raw) { o.r0 = scratch(); d.dst_raw0 = o.r0; if (b) { o.r1 = scratch(); d.dst_raw1 = o.r1; } }
-    if (split && also_raw) { o.rl0 = scratch(); d.dst_raw_lo0 = o.rl0; if (b) { o.rl1 = scratch(); d.dst_raw_lo1 = o.rl1; } }
-    if (split && !also_raw) { o.nl0 = scratch(); d.dst_lo0 = o.nl0; }
-    o.C0 = round_up(a.C, 16); o.C1 = b ? round_up(b->C, 16) : 0;
-    o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
+    if (o.also_raw) { o.r0 = scratch(); d.dst_raw0 = o.r0; if (b) { o.r1 = scratch(); d.dst_raw1 = o.r1; } }
+    if (o.split && o.also_raw) { o.rl0 = scratch(); d.dst_raw_lo0 = o.rl0; if (b) { o.rl1 = scratch(); d.dst_raw_lo1 = o.rl1; } }
+    if (o.split && !o.also_raw) { o.nl0 = scratch(); d.dst_lo0 = o.nl0; }
     Op op; op.kind = OP_PREP;
-    if (prep_fill(&d, &op.prep, &op.prep_nsrc)) { err = 1; return o; }
+    if (prep_fill(&d, &op.prep, &op.prep_nsrc)) { err = 1; return; }
     o.op = (int)pl->ops.size();
     pl->ops.push_back(op);
-    return o;
   }
 
-  void conv(const ConvW& cw, const Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats,
-            const ConvW* xproj = nullptr, const Operand* xin = nullptr) {
+  // the conv with its input transform inside the kernel (conv_fused.cuh); false: not applicable (the caller materialises)
+  bool try_fused(const ConvW& cw, Operand& in, int stride, const Tens* resid, Tens& out, bool out_stats, const ConvW* xproj, Operand* xin) {
+    if (!in.lazy || cw.precise || (xproj && !(xin && xin->lazy))) return false;
+    if (in.mode != 0 && (in.a.C / in.a.gs > 4 || (in.has_b && in.b.C / in.b.gs > 4))) return false;   // coefficient table: 4 groups per source
+    Op op; op.kind = OP_FUSED;
+    FusedParams& f = op.fused; memset(&f, 0, sizeof(f));
+    ConvParams& c = f.c;
+    const int Cmain = in.C0 + in.C1, Cx = xproj ? xin->C0 + xin->C1 : 0;
+    if (Cmain != cw.Cin || Cmain > kMaxCin || Cx > kMaxCin) return false;
+    c.Cin = Cmain; c.Cextra = 3 * Cx;
+    c.B = pl->B; c.H = in.H; c.W = in.W; c.taps = cw.taps; c.stride = stride;
+    if (stride == 2 && (c.H % 2 || c.W % 2)) return false;
+    c.wpk = reinterpret_cast<const __half*>(h->packed ? h->packed + cw.pk_off : (const uint8_t*)1); c.bias = P(cw.b_idx);
+    c.Cout = cw.Cout; c.CoutPad = cw.CoutPad;
+    if (xproj) { c.wpk_extra = reinterpret_cast<const __half*>(h->packed ? h->packed + xproj->pk_off : (const uint8_t*)1); c.bias_extra = P(xproj->b_idx); }
+    c.resid = resid ? (resid->data ? resid->data : (const float*)1) : nullptr; c.out = out.data ? out.data : (float*)1;
+    c.ostats = out_stats ? (out.stats ? out.stats : (double*)1) : nullptr; c.ogs = out.gs > 0 ? out.gs : cw.Cout;
+    if (out_stats && (cw.CoutPad > 64 || (cw.Cout != 16 && cw.Cout != 32 && cw.Cout != 64) || cw.Cout % c.ogs)) return false;
+    const Plc g = plc_geometry(pl->B, in.H, in.W);
+    c.PW = g.PW; c.PH = g.PH; c.Q = g.Q; c.G = g.G;
+    const int halo = cw.taps == 9 ? g.PW + 1 : 0;
+    c.P = kTileM + 2 * halo; c.Palloc = c.P | 1;
+    c.dPW.init(g.PW); c.dPH.init(g.PH);
+    c.num_tiles = (g.Q + kTileM - 1) / kTileM;
+    if (out_stats && g.PH * g.PW < 64) return false;                              // epilogue: a tile touches at most 3 images
+    if ((c.P - 1) / (g.PH * g.PW) + 2 > kFusedCoefSlots) return false;          // the halo window touches at most 4 images
+    const uint32_t w_bytes = conv_weight_bytes(cw.taps, c.Cin, c.Cextra, c.CoutPad);
+    const FusedSmem L = fused_smem_layout(w_bytes, Cmain, Cx, c.Palloc);
+    if (L.total > 227u * 1024u) return false;
+    f.coef_off = L.coef_off; f.a_off = L.a_off; f.xa_off = L.xa_off; f.w_off = L.w_off; f.slab_bytes = L.slab_bytes; f.xslab_bytes = L.xslab_bytes;
+    f.Cmain = Cmain; f.Cx = Cx;
+    auto src = [&](const Tens& t, int c_off, bool with_stats) {
+      FusedSrc q; q.src = t.data ? t.data : (const float*)1; q.C = t.C; q.stats = with_stats ? (t.stats ? t.stats : (const double*)1) : nullptr;
+      q.gs = t.gs > 0 ? t.gs : 8; q.c_offset = c_off; return q;
+    };
+    f.m[0] = src(in.a, 0, in.mode != 0); f.nm = 1;
+    if (in.has_b) { f.m[1] = src(in.b, in.a.C, in.mode != 0); f.nm = 2; }
+    f.mode = in.mode; f.act = in.silu ? 1 : 0; f.ups = in.upsample; f.Hs = in.a.H; f.Ws = in.a.W;
+    if (in.mode == 1) { f.film = pl->film ? pl->film : (const float*)1; f.film_stride = h->film_rows; f.film_off = in.film->off; f.film_ctot = in.a.C + (in.has_b ? in.b.C : 0); }
+    if (in.mode == 2) { f.gamma = P(in.gamma_idx) ? P(in.gamma_idx) : (const float*)1; f.beta = P(in.beta_idx) ? P(in.beta_idx) : (const float*)1; }
+    f.eps = kGnEps;
+    if (xproj) {
+      if (xin->upsample || xin->H != in.H || xin->W != in.W) return false;
+      f.x[0] = src(xin->a, 0, false); f.nx = 1;
+      if (xin->has_b) { f.x[1] = src(xin->b, xin->a.C, false); f.nx = 2; }
+    }
+    op.smem = L.total;
+    op.cols = cw.CoutPad <= 32 ? 32 : (cw.CoutPad <= 64 ? 64 : 128);
+    pl->ops.push_back(op);
+    return true;
+  }
+
+  void conv(const ConvW& cw, Operand& in, bool raw, int stride, const Tens* resid, Tens& out, bool out_stats,
+            const ConvW* xproj = nullptr, Operand* xin = nullptr) {
+    if (!raw && try_fused(cw, in, stride, resid, out, out_stats, xproj, xin)) return;
+    materialize(in);
+    if (xin) materialize(*xin);
+    if (err) return;
     dmd_conv_desc d; memset(&d, 0, sizeof(d));
     if (xproj) {  // skip projection of the block input, accumulated into this conv's output tile
       d.xsrc0 = xin->r0; d.xsrc0_lo = xin->rl0; d.xC0 = xin->C0;
@@ -844,11 +937,11 @@ struct PlanBuilder {
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
     Tens x = tensor(c.channels[0], H, W, true);
-    conv(conv_in, prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true), false, 1, nullptr, x, true);
+    { Operand in0 = prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true); conv(conv_in, in0, false, 1, nullptr, x, true); }
     for (int i = 0; i <= L; ++i) {
       if (i > 0 && i < L) {
         Tens xd = tensor(c.channels[i - 1], x.H / 2, x.W / 2, true);
-        conv(downs[i], prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false), false, 2, nullptr, xd, true);
+        { Operand ind = prep(x, nullptr, 0, 0, nullptr, 0, 0, false, false); conv(downs[i], ind, false, 2, nullptr, xd, true); }
         x = xd;
       }
       for (auto& rb : blocks[i]) x = resblock(rb, x, nullptr);
@@ -1215,6 +1308,10 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
     else if (op.kind == OP_PREP) {
       if (op.prep.film != nullptr && op.prep.film != film) { PrepParams pp = op.prep; pp.film = film; if (prep_launch(pp, op.prep_nsrc, st)) return 1; }
       else if (prep_launch(op.prep, op.prep_nsrc, st)) return 1;
+    }
+    else if (op.kind == OP_FUSED) {
+      if (op.fused.film != nullptr && op.fused.film != film) { FusedParams fp = op.fused; fp.film = film; if (fused_launch(fp, op.smem, op.cols, st)) return 1; }
+      else if (fused_launch(op.fused, op.smem, op.cols, st)) return 1;
     }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
@@ -2191,6 +2288,7 @@ extern "C" int dmd_rew_end_predict(dmd_rew_end* h, int b, int t, const float* ob
   for (const Op& op : pl.ops) {
     if (op.kind == OP_CONV) { if (conv_launch(op.conv, op.smem, op.cols, st)) return 1; }
     else if (op.kind == OP_PREP) { if (prep_launch(op.prep, op.prep_nsrc, st)) return 1; }
+    else if (op.kind == OP_FUSED) { if (fused_launch(op.fused, op.smem, op.cols, st)) return 1; }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
   // LSTM over time (torch.nn.LSTM, gate order i f g o), rows of step k are the contiguous block [k*b, (k+1)*b)

@@ -135,6 +135,167 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #define DMD_TS(role, it_, ev) do { } while (0)
 #endif
 
+// ------------------------------------------------------------------------------------------------------------------
+// Direct epilogue (shared by conv_tc_kernel and conv_fused_kernel): the eight epilogue warps read the accumulator with the
+// 16-lane x 256-bit TMEM pattern -- four neighbouring threads hold 32 contiguous bytes of one output row -- and store
+// (+bias, +residual) straight to NHWC global memory as full 32-byte sectors.  No shared-memory staging, no row table, no named
+// barriers; GroupNorm partial sums run in registers across the single-image tiles of a CTA and are reduced with shuffles.
+// Two warps share a TMEM lane quarter and split the columns; the host guarantees that all columns of a warp lie in ONE
+// GroupNorm group whenever statistics are requested (CoutPad <= 64).
+template <int kAccCols>
+struct DirectEpilogue {
+  int quarter, blk_begin, blk_end, lr, lc, G, my_grp, lane;
+  bool vec2;
+  float s0, s1, s2, ss0, ss1, ss2;
+  int n_cur;
+
+  __device__ __forceinline__ void init(const ConvParams& p, int warp, int lane_) {
+    lane = lane_;
+    const int ew = warp - 2;                   // 0..7
+    quarter = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                  // two warps share a quarter and split the columns
+    const int nblk = p.CoutPad >> 3;           // 8-column blocks of the accumulator
+    const int hb = (nblk + 1) >> 1;
+    blk_begin = half ? hb : 0; blk_end = half ? nblk : hb;
+    lr = lane >> 2; lc = (lane & 3) * 2;
+    vec2 = (p.Cout & 1) == 0;
+    G = p.ostats ? p.Cout / p.ogs : 1;
+    my_grp = p.ostats ? min(G - 1, (blk_begin * 8) / p.ogs) : 0;
+    s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+    n_cur = -1;
+  }
+
+  __device__ __forceinline__ void flush_stats(const ConvParams& p, int img0, bool multi) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+      ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+      if (multi) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
+      }
+    }
+    if (lane == 0) {
+      double* dst = p.ostats + ((size_t)img0 * G + my_grp) * 2;
+      if (img0 < p.B && (s0 != 0.f || ss0 != 0.f)) { atomicAdd(dst, (double)s0); atomicAdd(dst + 1, (double)ss0); }
+      if (multi) {
+        if (img0 + 1 < p.B && (s1 != 0.f || ss1 != 0.f)) { atomicAdd(dst + (size_t)G * 2, (double)s1); atomicAdd(dst + (size_t)G * 2 + 1, (double)ss1); }
+        if (img0 + 2 < p.B && (s2 != 0.f || ss2 != 0.f)) { atomicAdd(dst + (size_t)G * 4, (double)s2); atomicAdd(dst + (size_t)G * 4 + 1, (double)ss2); }
+      }
+    }
+    s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+  }
+
+  // one 128-row tile starting at padded-linear position q0; accumulator at TMEM address tmem_acc; tfull/parity: accumulator
+  // ready; tempty: arrived on (once per warp) as soon as the accumulator has been read
+  __device__ __forceinline__ void tile(const ConvParams& p, const float* sbias, uint32_t tmem_acc, int q0, uint64_t* tfull,
+                                       uint32_t parity, uint64_t* tempty) {
+    const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
+    const int q_last = min(q0 + kTileM, p.Q) - 1;
+    const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;
+    if (n_cur >= 0 && (!single_image || n_lo != n_cur)) { flush_stats(p, n_cur, false); n_cur = -1; }
+    // the four accumulator rows of this thread: j = 2*h + s -> row quarter*32 + 16*h + lane/4 + 8*s
+    int opix[4], slot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + quarter * 32 + (j >> 1) * 16 + lr + (j & 1) * 8;
+      opix[j] = -1; slot[j] = 0;
+      if (q < p.Q) {
+        const uint32_t R = p.dPW.div((uint32_t)q);
+        const int x = q - (int)R * p.PW;
+        const int n = (int)p.dPH.div(R);
+        const int y = (int)R - n * p.PH;
+        bool valid = (x < p.W) && (y < p.H);
+        int yo = y, xo = x, Ho = p.H, Wo = p.W;
+        if (p.stride == 2) {
+          valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
+          yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+        }
+        if (valid) { opix[j] = (n * Ho + yo) * Wo + xo; slot[j] = n - n_lo; }
+      }
+    }
+    bool waited = false;
+    auto chunk = [&](auto nbc, auto vecc, int blk) {
+      constexpr int NB = decltype(nbc)::value;
+      constexpr bool VEC = decltype(vecc)::value;   // even Cout: 8-byte accesses (every layer but conv_out / the 15-channel dgrad)
+      const int col0 = blk * 8 + lc;           // first of this thread's two columns in block 0 of the chunk
+      // residual first: it does not depend on the accumulator, so for the first chunk its latency hides behind the MMAs
+      float2 rr[4][NB];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          rr[j][k] = make_float2(0.f, 0.f);
+          const int col = col0 + 8 * k;
+          if (p.resid != nullptr && opix[j] >= 0 && col < p.Cout) {
+            const float* rp = p.resid + (size_t)opix[j] * p.Cout + col;
+            if (VEC) rr[j][k] = __ldg(reinterpret_cast<const float2*>(rp));
+            else { rr[j][k].x = __ldg(rp); if (col + 1 < p.Cout) rr[j][k].y = __ldg(rp + 1); }
+          }
+        }
+      if (!waited) {
+        mbar_wait(tfull, parity);
+        tc_fence_after_sync();
+        waited = true;
+      }
+      uint32_t r[8 * NB];
+      const uint32_t ta = tmem_acc + (uint32_t)(blk * 8) + ((uint32_t)(quarter * 32) << 16);
+      tmem_ld_16x256b_pair<NB>(ta, ta + (16u << 16), r);
+      if (blk + NB >= blk_end) {               // last chunk of this warp: the accumulator may be overwritten
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0 && tempty != nullptr) mbar_arrive(tempty);
+      }
+      float2 bv[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) bv[k] = (col0 + 8 * k < p.Cout) ? *reinterpret_cast<const float2*>(sbias + col0 + 8 * k) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (opix[j] >= 0) {
+          float* op = p.out + (size_t)opix[j] * p.Cout + col0;
+          float ps = 0.f, pss = 0.f;
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            if (col0 + 8 * k < p.Cout) {
+              const int ri = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1);
+              float2 o;
+              o.x = __uint_as_float(r[ri]) + bv[k].x + rr[j][k].x;
+              o.y = __uint_as_float(r[ri + 1]) + bv[k].y + rr[j][k].y;
+              if (VEC) *reinterpret_cast<float2*>(op + 8 * k) = o;
+              else { op[8 * k] = o.x; if (col0 + 8 * k + 1 < p.Cout) op[8 * k + 1] = o.y; }
+              ps += o.x + o.y;
+              pss = fmaf(o.x, o.x, fmaf(o.y, o.y, pss));
+            }
+          }
+          if (p.ostats != nullptr) {
+            const int sl = single_image ? 0 : slot[j];
+            s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
+            s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
+            s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
+          }
+        }
+      }
+    };
+    for (int blk = blk_begin; blk < blk_end;) {
+      const int rem = blk_end - blk;
+      if (!vec2) { chunk(std::integral_constant<int, 1>{}, std::false_type{}, blk); blk += 1; }   // odd Cout: narrow outputs only
+      else if (rem >= 4) { chunk(std::integral_constant<int, 4>{}, std::true_type{}, blk); blk += 4; }
+      else if (rem >= 2) { chunk(std::integral_constant<int, 2>{}, std::true_type{}, blk); blk += 2; }
+      else { chunk(std::integral_constant<int, 1>{}, std::true_type{}, blk); blk += 1; }
+    }
+    if (p.ostats != nullptr) {
+      if (single_image) n_cur = n_lo;            // keep running across the single-image tiles of this CTA
+      else { flush_stats(p, n_lo, true); n_cur = -1; }
+    }
+  }
+
+  __device__ __forceinline__ void finish(const ConvParams& p) {
+    if (n_cur >= 0) flush_stats(p, n_cur, false);
+  }
+};
+
 // kAccCols: TMEM columns per accumulator (>= CoutPad); two accumulators are allocated.
 // kGroups : epilogue organisation.  0: DIRECT -- the eight warps read the accumulator with the 16-lane x 256-bit TMEM pattern, whose
 //           register layout puts 32 contiguous bytes of an output row into four neighbouring threads, and store (+bias, +residual)
@@ -253,10 +414,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
       uint32_t tph0 = 1u, tph1 = 1u;  // parity to wait on for tempty[b]: first use passes immediately
+      // Barrier phases are probed ONE step ahead with a non-blocking test issued before the MMAs of the current slab: a
+      // blocking wait costs ~130 cycles even on a completed phase, and the thread would pay it between every two slabs while the
+      // tensor pipe drains.  `rdy` / `trdy` carry the result of the probe; the blocking wait remains as the fallback.
+      bool rdy = mbar_test(full + 0, 0u);
+      bool trdy = true;               // tempty[0], first use
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         DMD_TS(1, it, 12);
-        mbar_wait(tempty + b, b ? tph1 : tph0);
+        if (!trdy) mbar_wait(tempty + b, b ? tph1 : tph0);
         DMD_TS(1, it, 13);
         if (b) tph1 ^= 1u; else tph0 ^= 1u;
         tc_fence_after_sync();
@@ -264,9 +430,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         uint32_t b_lo = b_lo0;
         for (int ks = 0; ks < kslabs; ++ks) {
           DMD_TS(1, it, (ks & 3) * 3 + 0);
-          mbar_wait(full + stage, phase);
+          if (!rdy) mbar_wait(full + stage, phase);
           DMD_TS(1, it, (ks & 3) * 3 + 1);
           tc_fence_after_sync();
+          {  // probe the next slab (and, on the last slab of a tile, the next accumulator) before issuing
+            uint32_t ns = stage + 1, np = phase;
+            if (ns == (uint32_t)S) { ns = 0; np ^= 1u; }
+            rdy = mbar_test(full + ns, np);
+            if (ks == kslabs - 1) trdy = mbar_test(tempty + (b ^ 1), (b ^ 1) ? tph1 : tph0);
+          }
           if (elect_one_sync()) {
             if (!DMD_DBG(2)) {
               if (ks >= main_slabs) {
@@ -303,143 +475,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   } else {
     // =========================================================================================== EPILOGUE (8 warps)
     if constexpr (kGroups == 0) {
-      // ---- direct epilogue: TMEM (16 lanes x 256 bit pattern) -> registers -> (+bias, +residual) -> global, statistics by shuffles
-      const int ew = warp - 2;                   // 0..7
-      const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-      const int half = ew >> 2;                  // two warps share a quarter and split the columns
-      const int nblk = p.CoutPad >> 3;           // 8-column blocks of the accumulator
-      const int hb = (nblk + 1) >> 1;
-      const int blk_begin = half ? hb : 0, blk_end = half ? nblk : hb;
-      const int lr = lane >> 2, lc = (lane & 3) * 2;
-      const bool vec2 = (p.Cout & 1) == 0;
-      const int G = p.ostats ? p.Cout / p.ogs : 1;
-      const int my_grp = p.ostats ? min(G - 1, (blk_begin * 8) / p.ogs) : 0;   // host: all columns of a warp lie in ONE group
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss0 = 0.f, ss1 = 0.f, ss2 = 0.f;
-      int n_cur = -1;
-      auto flush_stats = [&](int img0, bool multi) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-          ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
-          if (multi) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-            ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-            ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
-          }
-        }
-        if (lane == 0) {
-          double* dst = p.ostats + ((size_t)img0 * G + my_grp) * 2;
-          if (img0 < p.B && (s0 != 0.f || ss0 != 0.f)) { atomicAdd(dst, (double)s0); atomicAdd(dst + 1, (double)ss0); }
-          if (multi) {
-            if (img0 + 1 < p.B && (s1 != 0.f || ss1 != 0.f)) { atomicAdd(dst + (size_t)G * 2, (double)s1); atomicAdd(dst + (size_t)G * 2 + 1, (double)ss1); }
-            if (img0 + 2 < p.B && (s2 != 0.f || ss2 != 0.f)) { atomicAdd(dst + (size_t)G * 4, (double)s2); atomicAdd(dst + (size_t)G * 4 + 1, (double)ss2); }
-          }
-        }
-        s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
-      };
+      // ---- direct epilogue: TMEM (16 lanes x 256 bit pattern) -> registers -> (+bias, +residual) -> global (DirectEpilogue above)
+      DirectEpilogue<kAccCols> epi;
+      epi.init(p, warp, lane);
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
-        const int q0 = (tile_begin + it) * kTileM;
-        const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q0));
-        const int q_last = min(q0 + kTileM, p.Q) - 1;
-        const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;
-        if (n_cur >= 0 && (!single_image || n_lo != n_cur)) { flush_stats(n_cur, false); n_cur = -1; }
-        // the four accumulator rows of this thread: j = 2*h + s -> row quarter*32 + 16*h + lane/4 + 8*s
-        int opix[4], slot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int q = q0 + quarter * 32 + (j >> 1) * 16 + lr + (j & 1) * 8;
-          opix[j] = -1; slot[j] = 0;
-          if (q < p.Q) {
-            const uint32_t R = p.dPW.div((uint32_t)q);
-            const int x = q - (int)R * p.PW;
-            const int n = (int)p.dPH.div(R);
-            const int y = (int)R - n * p.PH;
-            bool valid = (x < p.W) && (y < p.H);
-            int yo = y, xo = x, Ho = p.H, Wo = p.W;
-            if (p.stride == 2) {
-              valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
-              yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
-            }
-            if (valid) { opix[j] = (n * Ho + yo) * Wo + xo; slot[j] = n - n_lo; }
-          }
-        }
-        bool waited = false;
-        auto chunk = [&](auto nbc, auto vecc, int blk) {
-          constexpr int NB = decltype(nbc)::value;
-          constexpr bool VEC = decltype(vecc)::value;   // even Cout: 8-byte accesses (every layer but conv_out / the 15-channel dgrad)
-          const int col0 = blk * 8 + lc;           // first of this thread's two columns in block 0 of the chunk
-          // residual first: it does not depend on the accumulator, so for the first chunk its latency hides behind the MMAs
-          float2 rr[4][NB];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-              rr[j][k] = make_float2(0.f, 0.f);
-              const int col = col0 + 8 * k;
-              if (p.resid != nullptr && opix[j] >= 0 && col < p.Cout) {
-                const float* rp = p.resid + (size_t)opix[j] * p.Cout + col;
-                if (VEC) rr[j][k] = __ldg(reinterpret_cast<const float2*>(rp));
-                else { rr[j][k].x = __ldg(rp); if (col + 1 < p.Cout) rr[j][k].y = __ldg(rp + 1); }
-              }
-            }
-          if (!waited) {
-            mbar_wait(tfull + b, ((uint32_t)it >> 1) & 1u);
-            tc_fence_after_sync();
-            waited = true;
-          }
-          uint32_t r[8 * NB];
-          const uint32_t ta = tmem_base + (uint32_t)b * kAccCols + (uint32_t)(blk * 8) + ((uint32_t)(quarter * 32) << 16);
-          tmem_ld_16x256b_pair<NB>(ta, ta + (16u << 16), r);
-          if (blk + NB >= blk_end) {               // last chunk of this warp: the accumulator may be overwritten
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + b);
-          }
-          float2 bv[NB];
-#pragma unroll
-          for (int k = 0; k < NB; ++k) bv[k] = (col0 + 8 * k < p.Cout) ? *reinterpret_cast<const float2*>(sbias + col0 + 8 * k) : make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (opix[j] >= 0) {
-              float* op = p.out + (size_t)opix[j] * p.Cout + col0;
-              float ps = 0.f, pss = 0.f;
-#pragma unroll
-              for (int k = 0; k < NB; ++k) {
-                if (col0 + 8 * k < p.Cout) {
-                  const int ri = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1);
-                  float2 o;
-                  o.x = __uint_as_float(r[ri]) + bv[k].x + rr[j][k].x;
-                  o.y = __uint_as_float(r[ri + 1]) + bv[k].y + rr[j][k].y;
-                  if (VEC) *reinterpret_cast<float2*>(op + 8 * k) = o;
-                  else { op[8 * k] = o.x; if (col0 + 8 * k + 1 < p.Cout) op[8 * k + 1] = o.y; }
-                  ps += o.x + o.y;
-                  pss = fmaf(o.x, o.x, fmaf(o.y, o.y, pss));
-                }
-              }
-              if (p.ostats != nullptr) {
-                const int sl = single_image ? 0 : slot[j];
-                s0 += (sl == 0) ? ps : 0.f;  ss0 += (sl == 0) ? pss : 0.f;
-                s1 += (sl == 1) ? ps : 0.f;  ss1 += (sl == 1) ? pss : 0.f;
-                s2 += (sl == 2) ? ps : 0.f;  ss2 += (sl == 2) ? pss : 0.f;
-              }
-            }
-          }
-        };
-        for (int blk = blk_begin; blk < blk_end;) {
-          const int rem = blk_end - blk;
-          if (!vec2) { chunk(std::integral_constant<int, 1>{}, std::false_type{}, blk); blk += 1; }   // odd Cout: narrow outputs only
-          else if (rem >= 4) { chunk(std::integral_constant<int, 4>{}, std::true_type{}, blk); blk += 4; }
-          else if (rem >= 2) { chunk(std::integral_constant<int, 2>{}, std::true_type{}, blk); blk += 2; }
-          else { chunk(std::integral_constant<int, 1>{}, std::true_type{}, blk); blk += 1; }
-        }
-        if (p.ostats != nullptr) {
-          if (single_image) n_cur = n_lo;            // keep running across the single-image tiles of this CTA
-          else { flush_stats(n_lo, true); n_cur = -1; }
-        }
+        epi.tile(p, sbias, tmem_base + (uint32_t)b * kAccCols, (tile_begin + it) * kTileM, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b);
       }
-      if (n_cur >= 0) flush_stats(n_cur, false);
+      epi.finish(p);
     } else {
     constexpr int GT = kEpiThreads / (kGroups ? kGroups : 1);  // threads per epilogue group
     constexpr int GW = kEpiWarps / (kGroups ? kGroups : 1);    // warps per group (8 or 4): GW / 4 warps share one TMEM lane quarter

@@ -15,3 +15,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _bounded_cpu_threads():
+    """The CPU oracle (torch convolutions on 64x64 images) is fastest with 8-16 intra-op threads and collapses on the 100+
+    cores of a GPU box; every test that runs it gets a bounded pool."""
+    import torch
+
+    torch.set_num_threads(min(16, max(1, os.cpu_count() or 1)))
+    yield

@@ -157,7 +157,7 @@ def test_denoiser_vs_oracle_fresh_inputs_and_weight_update():
     obs, act, x_noisy = O.synthetic_inputs(5, inner, 64, 64, 4242)
     b, t, ch, h, w = obs.shape
     sig = torch.tensor([0.002, 0.3, 1.0, 5.0, 20.0])
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(min(16, max(1, os.cpu_count() or 1)))  # torch CPU convs on these small images collapse with very many threads
     with torch.no_grad():
         ref = O.model_output(x_noisy, sig, obs.reshape(b, t * ch, h, w), act, sd, cfg)
     model, _ = den._native_forward(x_noisy.to(dev), sig.to(dev), obs.reshape(b, t * ch, h, w).to(dev), act.to(dev), True, False)
@@ -187,7 +187,7 @@ def test_benchmarked_batch_sizes_match_the_oracle(b):
     den, sd = _build(inner, 2024, dev)   # the weights bench.py uses (PCG64 seed 2024)
     cfg = O.DenoiserCfg(inner=inner)
     obs, act, x0 = O.synthetic_inputs(b, inner, 64, 64, 100)   # bench.py rank-0 inputs
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(min(16, max(1, os.cpu_count() or 1)))  # torch CPU convs on these small images collapse with very many threads
     t, ch = inner.num_steps_conditioning, inner.img_channels
     flat = obs.reshape(b, t * ch, 64, 64)
     sig = torch.full((b,), 5.0) if b == 1 else torch.linspace(0.002, 20.0, b)
