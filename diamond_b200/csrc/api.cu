@@ -162,6 +162,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
   const int halo = d->taps == 9 ? g.PW + 1 : 0;
   p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
+  if (tune_int("DMD_CONV_PALLOC8", 0)) p->Palloc = round_up(p->P, 8);   // experiment: 128-byte aligned slab / chunk bases
   if (d->out_stats) {
     const int L4 = d->Cout / 4;
     DMD_CHECK(g.PH * g.PW >= 64, "conv: image too small for the statistics epilogue (a tile may touch at most %d images)", kStatSlots);
@@ -225,6 +226,8 @@ static int init_kernels() {
     DMD_CUDA(cudaFuncSetAttribute(conv_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -321,7 +324,22 @@ static int prep_launch(const PrepParams& p0, int nsrc, cudaStream_t st) {
     const long long total = (long long)p.Qalloc * (p.s[0].Cpad >> 3);
     return launch_pdl(zero_insert_prep_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
   }
-  return launch_pdl(prep_act_kernel, dim3((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc), dim3(kPrepThreads), 0, st, p);
+  const dim3 grid((p.Qalloc + p.pos_per_block - 1) / p.pos_per_block, 1, nsrc);
+  // the hot cases (norm + SiLU, no upsample, no low part of the normalised operand; raw + raw-low on every source or on none)
+  // run on the lean kernel; everything else on the generic one
+  bool fast = tune_int("DMD_PREP_FAST", 1) != 0 && p.mode != 0 && p.act && p.ups == 0;
+  const bool raw = p.s[0].dst_raw != nullptr;
+  for (int k = 0; k < nsrc && fast; ++k) {
+    const PrepSrc& S = p.s[k];
+    if (S.dst_lo != nullptr || (S.dst_raw != nullptr) != raw || (S.dst_raw_lo != nullptr) != raw || S.Cpad != p.s[0].Cpad || S.C % 8 != 0) fast = false;
+  }
+  if (fast && (long long)p.B * p.Hs * p.Ws * (p.s[0].C > p.s[nsrc - 1].C ? p.s[0].C : p.s[nsrc - 1].C) >= (1ll << 31)) fast = false;   // 32-bit source indices
+  if (fast) {
+    const int nch = p.s[0].Cpad >> 3;
+    if (nch == 8) return raw ? launch_pdl(prep_fast_kernel<8, true>, grid, dim3(kPrepThreads), 0, st, p) : launch_pdl(prep_fast_kernel<8, false>, grid, dim3(kPrepThreads), 0, st, p);
+    if (nch == 4) return raw ? launch_pdl(prep_fast_kernel<4, true>, grid, dim3(kPrepThreads), 0, st, p) : launch_pdl(prep_fast_kernel<4, false>, grid, dim3(kPrepThreads), 0, st, p);
+  }
+  return launch_pdl(prep_act_kernel, grid, dim3(kPrepThreads), 0, st, p);
 }
 extern "C" int dmd_prep_plan(const dmd_prep_desc* d, int* blocks, int* pos_per_block, int* sources) {
   DMD_CHECK(d && blocks && pos_per_block && sources, "prep_plan: null argument");
@@ -486,6 +504,15 @@ static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * p.C + 4));
   AttnParams pt = p;
   pt.ktrace = kt_slot("attn", B, p.C);
+  if (tune_int("DMD_ATTN_CLUSTER", 1) != 0 && p.gs % (p.C / 4) == 0) {
+    // four CTAs per image (thread-block cluster), distributed shared memory for the head outputs
+    const int CH = p.C / 4;
+    const size_t csmem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * CH + 4) + (size_t)p.L * CH);
+    if (p.C == 64) attn_cluster_kernel<64><<<4 * B, kAttnCThreads, csmem, st>>>(pt);
+    else attn_cluster_kernel<32><<<4 * B, kAttnCThreads, csmem, st>>>(pt);
+    DMD_LAUNCH_OK();
+    return 0;
+  }
   if (p.C == 64) attn_kernel<64><<<B, kAttnThreads, smem, st>>>(pt);
   else attn_kernel<32><<<B, kAttnThreads, smem, st>>>(pt);
   DMD_LAUNCH_OK();
@@ -784,11 +811,12 @@ struct PlanBuilder {
     o.upsample = upsample; o.mode = mode; o.film = film; o.gamma_idx = gamma_idx; o.beta_idx = beta_idx; o.silu = silu; o.also_raw = also_raw; o.split = split;
     o.C0 = round_up(a.C, 16); o.C1 = b ? round_up(b->C, 16) : 0;
     o.H = upsample ? 2 * a.H : a.H; o.W = upsample ? 2 * a.W : a.W;
-    // small problems (at most one tile per SM): leave the transform to the consuming conv (conv_fused_kernel); never in
+    // small problems (at most one tile per SM) may leave the transform to the consuming conv (conv_fused_kernel, DMD_FUSE_SMALL=1;
+    // measured in the CUDA graph at B=32: one 8.7 us launch instead of 4.0 + 4.6 us -- no gain yet, so it is opt-in); never in
     // training plans, whose backward replays the prep launches
     const Plc g = plc_geometry(pl->B, o.H, o.W);
     const int tiles = (g.Q + kTileM - 1) / kTileM;
-    o.lazy = !pl->train && g_num_sms > 0 && tiles <= g_num_sms && tune_int("DMD_FUSE_SMALL", 1) != 0 && upsample != 2 &&
+    o.lazy = !pl->train && g_num_sms > 0 && tiles <= g_num_sms && tune_int("DMD_FUSE_SMALL", 0) != 0 && upsample != 2 &&
              a.C % 16 == 0 && (!b || b->C % 16 == 0);
     if (!o.lazy) materialize(o);
     return o;

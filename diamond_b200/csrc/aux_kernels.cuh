@@ -2,6 +2,7 @@
 // Each kernel cites the reference lines it replaces.  No fast-math: sqrt / div are IEEE so the EDM conditioners and
 // the uint8 quantiser reproduce the reference's fp32 arithmetic bit for bit where it matters (denoiser.py:66-84).
 #pragma once
+#include <cooperative_groups.h>
 #include "ptx.cuh"
 
 namespace dmd {
@@ -356,6 +357,174 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnParams p) 
       }
       if ((tid & 31) == 0) {
         const int g = (og * NO2) / p.gs;
+        atomicAdd(p.ostats + ((size_t)n * G + g) * 2, (double)a);
+        atomicAdd(p.ostats + ((size_t)n * G + g) * 2 + 1, (double)b);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SelfAttention2d on a CLUSTER of four CTAs per image (same math as attn_kernel above, same parameter block).
+// The one-CTA-per-image kernel keeps 32 of 148 SMs busy at the benchmark batch and runs ~5 k instructions per thread
+// (32 us in the CUDA graph: 5 % of a sample()).  Here cluster rank r owns C/4 channels = C/32 heads:
+//   every CTA   : GroupNorm(x) for all channels (its q/k/v rows contract over all of them)
+//   rank r      : q, k, v rows of its heads -> softmax(q k^T / sqrt(d)) v with the 64 keys split over 2 (C=64) or 4 (C=32)
+//                 threads per (head, query) and merged with shuffles -> its C/4 channels of y in ITS shared memory
+//   cluster.sync, then every CTA reads the other three y slices through distributed shared memory and computes ITS C/4
+//   output channels of out_proj(y) + xn (blocks.py:72: the residual is the NORMED x), plus their GroupNorm partial sums.
+// 256 threads per CTA, 4 * B CTAs.
+constexpr int kAttnCThreads = 256;
+
+template <int C>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kAttnCThreads) attn_cluster_kernel(const AttnParams p) {
+  namespace cg = cooperative_groups;
+  constexpr int L = kAttnL, XP = C + 1, CH = C / 4, HL = CH / 8;      // CH channels / HL heads per CTA
+  constexpr int Q3 = 3 * CH, QP = Q3 + 4;                            // local q | k | v row, float4-addressable
+  constexpr int KS = kAttnCThreads / (HL * L);                       // threads per (head, query): 2 (C=64) or 4 (C=32)
+  constexpr int KPT = L / KS;                                        // keys per thread
+  extern __shared__ __align__(16) float sm_attn[];
+  float* xs = sm_attn;              // [L][XP]  normed x
+  float* qkv = xs + L * XP;         // [L][QP]  local q, k, v
+  float* ys = qkv + L * QP;         // [L][CH]  local y (read by the other ranks)
+  float* ya = ys + L * CH;          // [L][XP]  all channels of y
+  __shared__ float smr[8][2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = (int)cluster.block_rank();
+  const int n = blockIdx.x >> 2, tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) ktrace_stamp(p.ktrace);
+  const int G = C / p.gs;
+  if (tid < G) {
+    const double cnt = (double)L * p.gs;
+    const double mean = p.st_in[((size_t)n * G + tid) * 2] / cnt;
+    double var = p.st_in[((size_t)n * G + tid) * 2 + 1] / cnt - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    smr[tid][0] = (float)mean;
+    smr[tid][1] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
+  const float* xg = p.x + (size_t)n * L * C;
+  for (int i = tid; i < L * C; i += kAttnCThreads) {
+    const int l = i / C, c = i - l * C;
+    const int g = c / p.gs;
+    xs[l * XP + c] = (xg[i] - smr[g][0]) * smr[g][1] * __ldg(p.gamma + c) + __ldg(p.beta + c);
+  }
+  __syncthreads();
+  // ---- local q | k | v rows: thread = (token l, output group og of NO outputs)
+  {
+    constexpr int NG = kAttnCThreads / L;   // 4
+    constexpr int NO = Q3 / NG;             // 12 (C=64) or 6 (C=32)
+    const int l = tid % L, og = tid / L;
+    float acc[NO];
+    int row[NO];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      const int j = og * NO + i, part = j / CH, cc = j - part * CH;
+      row[i] = part * C + r * CH + cc;      // row of the [3C][C] in-projection (q rows, then k rows, then v rows)
+      acc[i] = __ldg(p.bqkv + row[i]);
+    }
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float x0 = xs[l * XP + 4 * c4], x1 = xs[l * XP + 4 * c4 + 1], x2 = xs[l * XP + 4 * c4 + 2], x3 = xs[l * XP + 4 * c4 + 3];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wqkv + (size_t)row[i] * C) + c4);
+        acc[i] = fmaf(w.x, x0, acc[i]); acc[i] = fmaf(w.y, x1, acc[i]);
+        acc[i] = fmaf(w.z, x2, acc[i]); acc[i] = fmaf(w.w, x3, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NO; ++i) qkv[l * QP + og * NO + i] = acc[i];
+  }
+  __syncthreads();
+  // ---- attention: item = (local head hl, query l), KS neighbouring lanes split the keys and merge (max, sum, y) by shuffles
+  {
+    const int item = tid / KS, part = tid % KS;
+    const int hl = item / L, l = item - hl * L;
+    float q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = qkv[l * QP + hl * 8 + e] * 0.35355339059327373f;  // 1/sqrt(8)
+    float sc[KPT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < KPT; ++jj) {
+      const int j = part * KPT + jj;
+      const float4 k0 = *reinterpret_cast<const float4*>(qkv + j * QP + CH + hl * 8);
+      const float4 k1 = *reinterpret_cast<const float4*>(qkv + j * QP + CH + hl * 8 + 4);
+      float sj = q[0] * k0.x;
+      sj = fmaf(q[1], k0.y, sj); sj = fmaf(q[2], k0.z, sj); sj = fmaf(q[3], k0.w, sj);
+      sj = fmaf(q[4], k1.x, sj); sj = fmaf(q[5], k1.y, sj); sj = fmaf(q[6], k1.z, sj); sj = fmaf(q[7], k1.w, sj);
+      sc[jj] = sj;
+      mx = fmaxf(mx, sj);
+    }
+#pragma unroll
+    for (int m = 1; m < KS; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));   // the row maximum over all 64 keys
+    float den = 0.f;
+    float y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int jj = 0; jj < KPT; ++jj) {
+      const int j = part * KPT + jj;
+      const float pj = expf(sc[jj] - mx);
+      den += pj;
+      const float4 v0 = *reinterpret_cast<const float4*>(qkv + j * QP + 2 * CH + hl * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(qkv + j * QP + 2 * CH + hl * 8 + 4);
+      y[0] = fmaf(pj, v0.x, y[0]); y[1] = fmaf(pj, v0.y, y[1]); y[2] = fmaf(pj, v0.z, y[2]); y[3] = fmaf(pj, v0.w, y[3]);
+      y[4] = fmaf(pj, v1.x, y[4]); y[5] = fmaf(pj, v1.y, y[5]); y[6] = fmaf(pj, v1.z, y[6]); y[7] = fmaf(pj, v1.w, y[7]);
+    }
+#pragma unroll
+    for (int m = 1; m < KS; m <<= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] += __shfl_xor_sync(0xffffffffu, y[e], m);
+    }
+    if (part == 0) {
+      const float inv = 1.0f / den;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ys[l * CH + hl * 8 + e] = y[e] * inv;
+    }
+  }
+  cluster.sync();   // every rank's y slice is complete and visible cluster-wide
+  // ---- gather all channels of y (three slices through distributed shared memory)
+  for (int i = tid; i < L * C; i += kAttnCThreads) {
+    const int l = i / C, c = i - l * C;
+    const int src = c / CH;
+    const float* remote = cluster.map_shared_rank(ys, src);
+    ya[l * XP + c] = remote[l * CH + (c - src * CH)];
+  }
+  cluster.sync();   // nobody leaves (or overwrites ys) while its slice is still being read
+  // ---- out projection of THIS rank's channels + residual on normed x; statistics.  thread = (token l, NO2 outputs)
+  {
+    constexpr int NG = kAttnCThreads / L;   // 4
+    constexpr int NO2 = CH / NG;            // 4 (C=64) or 2 (C=32) consecutive outputs
+    const int l = tid % L, og = tid / L;
+    const int oc0 = r * CH + og * NO2;
+    float acc[NO2];
+#pragma unroll
+    for (int i = 0; i < NO2; ++i) acc[i] = __ldg(p.bout + oc0 + i);
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float y0 = ya[l * XP + 4 * c4], y1 = ya[l * XP + 4 * c4 + 1], y2 = ya[l * XP + 4 * c4 + 2], y3 = ya[l * XP + 4 * c4 + 3];
+#pragma unroll
+      for (int i = 0; i < NO2; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wout + (size_t)(oc0 + i) * C) + c4);
+        acc[i] = fmaf(w.x, y0, acc[i]); acc[i] = fmaf(w.y, y1, acc[i]);
+        acc[i] = fmaf(w.z, y2, acc[i]); acc[i] = fmaf(w.w, y3, acc[i]);
+      }
+    }
+    float* og_ptr = p.out + (size_t)n * L * C + (size_t)l * C + oc0;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < NO2; ++i) {
+      const float v = xs[l * XP + oc0 + i] + acc[i];
+      og_ptr[i] = v;
+      a += v; b += v * v;
+    }
+    if (p.ostats) {   // all channels of a CTA lie in one GroupNorm group (CH <= gs, gs a multiple of CH)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+      }
+      if ((tid & 31) == 0) {
+        const int g = (r * CH) / p.gs;
         atomicAdd(p.ostats + ((size_t)n * G + g) * 2, (double)a);
         atomicAdd(p.ostats + ((size_t)n * G + g) * 2 + 1, (double)b);
       }

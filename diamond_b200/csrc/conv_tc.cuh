@@ -414,15 +414,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       }
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
       uint32_t tph0 = 1u, tph1 = 1u;  // parity to wait on for tempty[b]: first use passes immediately
-      // Barrier phases are probed ONE step ahead with a non-blocking test issued before the MMAs of the current slab: a
-      // blocking wait costs ~130 cycles even on a completed phase, and the thread would pay it between every two slabs while the
-      // tensor pipe drains.  `rdy` / `trdy` carry the result of the probe; the blocking wait remains as the fallback.
-      bool rdy = mbar_test(full + 0, 0u);
-      bool trdy = true;               // tempty[0], first use
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         DMD_TS(1, it, 12);
-        if (!trdy) mbar_wait(tempty + b, b ? tph1 : tph0);
+        mbar_wait(tempty + b, b ? tph1 : tph0);
         DMD_TS(1, it, 13);
         if (b) tph1 ^= 1u; else tph0 ^= 1u;
         tc_fence_after_sync();
@@ -430,15 +425,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         uint32_t b_lo = b_lo0;
         for (int ks = 0; ks < kslabs; ++ks) {
           DMD_TS(1, it, (ks & 3) * 3 + 0);
-          if (!rdy) mbar_wait(full + stage, phase);
+          mbar_wait(full + stage, phase);
           DMD_TS(1, it, (ks & 3) * 3 + 1);
           tc_fence_after_sync();
-          {  // probe the next slab (and, on the last slab of a tile, the next accumulator) before issuing
-            uint32_t ns = stage + 1, np = phase;
-            if (ns == (uint32_t)S) { ns = 0; np ^= 1u; }
-            rdy = mbar_test(full + ns, np);
-            if (ks == kslabs - 1) trdy = mbar_test(tempty + (b ^ 1), (b ^ 1) ? tph1 : tph0);
-          }
           if (elect_one_sync()) {
             if (!DMD_DBG(2)) {
               if (ks >= main_slabs) {
@@ -449,7 +438,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
               } else if (nine) {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                  const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + shift[t]);
+                  const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (DMD_DBG(16) ? 0u : shift[t]));   // dbg 16: every tap at the (aligned) slab base -- timing experiment, wrong results
                   const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + b_tap[t]);
                   umma_f16(d_tmem, ad, bd, idesc, (ks | t) != 0 ? 1u : 0u);
                 }
@@ -883,6 +872,137 @@ __global__ void __launch_bounds__(kPrepThreads, 4) prep_act_kernel(const PrepPar
     pl += kPrepBatch * pstep;
     if (pl >= p.pos_per_block) break;
     load_batch();
+  }
+}
+
+// prep_fast_kernel: the hot cases of prep_act_kernel with everything else compiled out -- GroupNorm / AdaGroupNorm + SiLU, no
+// upsample, no low part of the normalised operand; RAW additionally emits the raw operand and its low part (the split-fp16
+// operand of the fused 1x1 skip projection).  prep_act_kernel executes ~225 instructions per 8-channel item (ncu: 7.6 M
+// warp-instructions per 64x64x64-channel launch, issue-bound), most of them generic-path bookkeeping: here the chunk count is a
+// template parameter, a thread owns ONE 8-channel chunk and walks positions, addresses are 32-bit, and four items are in flight
+// per thread.  Same grid, same PrepParams, bit-identical results.
+template <int NCH, bool RAW>
+__global__ void __launch_bounds__(kPrepThreads, 4) prep_fast_kernel(const PrepParams p) {
+  __shared__ float sa[2][kMaxCin], sb[2][kMaxCin];  // coefficients for the (at most 2) images this block touches
+  __shared__ float smr[2][4][2];                    // (mean, rstd) per (image slot, group)
+  constexpr int PSTEP = kPrepThreads / NCH;
+  constexpr int kBatch = 4;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) ktrace_stamp(p.ktrace);
+  const PrepSrc& S = p.s[blockIdx.z];
+  const int pa0 = blockIdx.x * p.pos_per_block;     // first allocation position of this block
+  const int q_first = pa0 - p.G;
+  const int n0 = q_first > 0 ? (int)p.dPH.div(p.dPW.div((uint32_t)min(q_first, p.Q - 1))) : 0;
+  const int j = threadIdx.x & (NCH - 1);
+  int pl = threadIdx.x / NCH;
+  int x, y, n;                                      // coordinates of position pa0 + pl (x < 0: still inside the front guard)
+  {
+    const int q = pa0 + pl - p.G;
+    const int qq = q < 0 ? 0 : q;
+    const uint32_t R = p.dPW.div((uint32_t)qq);
+    x = qq - (int)R * p.PW; n = (int)p.dPH.div(R); y = (int)R - n * p.PH;
+    if (q < 0) x += q;
+  }
+  const bool has_data = j * 8 < S.C;
+  // ---- statistics -> coefficients (identical to prep_act_kernel)
+  {
+    const int G = S.C / S.gs;
+    if (threadIdx.x < 2 * G) {
+      const int slot = threadIdx.x / G, g = threadIdx.x - slot * G;
+      const int ni = n0 + slot;
+      float mean_f = 0.f, rstd_f = 0.f;
+      if (ni < p.B) {
+        const double* st = S.stats + ((size_t)ni * G + g) * 2;
+        const double cnt = (double)p.Hs * p.Ws * S.gs;
+        const double mean = st[0] / cnt;
+        double var = st[1] / cnt - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        mean_f = (float)mean;
+        rstd_f = (float)(1.0 / sqrt(var + (double)p.eps));
+      }
+      smr[slot][g][0] = mean_f;
+      smr[slot][g][1] = rstd_f;
+    }
+    float sc[2] = {0.f, 0.f}, sh[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = threadIdx.x + k * kPrepThreads;
+      if (e < 2 * S.C) {
+        const int slot = e / S.C, c = e - slot * S.C;
+        const int ni = n0 + slot, cg = S.c_offset + c;
+        if (ni < p.B) {
+          if (p.mode == 1) {
+            const float* f = p.film + (size_t)ni * p.film_stride + p.film_off;
+            sc[k] = 1.f + __ldg(f + cg);
+            sh[k] = __ldg(f + p.film_ctot + cg);
+          } else {
+            sc[k] = __ldg(p.gamma + cg);
+            sh[k] = __ldg(p.beta + cg);
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = threadIdx.x + k * kPrepThreads;
+      if (e < 2 * S.C) {
+        const int slot = e / S.C, c = e - slot * S.C;
+        const float mean = smr[slot][c / S.gs][0], rstd = smr[slot][c / S.gs][1];
+        const float a = rstd * sc[k];
+        sa[slot][c] = a;
+        sb[slot][c] = sh[k] - mean * a;
+      }
+    }
+    __syncthreads();
+  }
+  uint8_t* const d_n = S.dst + (size_t)j * p.plane_bytes + (size_t)pa0 * 16;
+  uint8_t* const d_r = RAW ? S.dst_raw + (size_t)j * p.plane_bytes + (size_t)pa0 * 16 : nullptr;
+  uint8_t* const d_rl = RAW ? S.dst_raw_lo + (size_t)j * p.plane_bytes + (size_t)pa0 * 16 : nullptr;
+  const int limit = min(p.pos_per_block, p.Qalloc - pa0);   // positions this block writes
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (; pl < limit; pl += kBatch * PSTEP) {
+    float4 v0[kBatch], v1[kBatch];
+    int slot[kBatch];                                // -1: zero fill
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      slot[u] = -1;
+      if (pl + u * PSTEP < limit && has_data && x >= 0 && x < p.W && y < p.H && n < p.B) {
+        const uint32_t idx = (uint32_t)((n * p.Hs + y) * p.Ws + x) * (uint32_t)S.C + (uint32_t)(j * 8);
+        const float4* gp = reinterpret_cast<const float4*>(S.src + idx);
+        v0[u] = __ldg(gp); v1[u] = __ldg(gp + 1);
+        slot[u] = n - n0;
+      }
+      x += PSTEP;
+      while (x >= p.PW) { x -= p.PW; if (++y == p.PH) { y = 0; ++n; } }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int pp = pl + u * PSTEP;
+      if (pp >= limit) break;
+      uint4 packed = zero4, raw = zero4, raw_lo = zero4;
+      if (slot[u] >= 0) {
+        const float4* pa4 = reinterpret_cast<const float4*>(&sa[slot[u]][j * 8]);
+        const float4* pb4 = reinterpret_cast<const float4*>(&sb[slot[u]][j * 8]);
+        const float4 a0 = pa4[0], a1 = pa4[1], b0 = pb4[0], b1 = pb4[1];
+        const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+        if (RAW) {
+          raw.x = pack_h2(v[0], v[1]); raw.y = pack_h2(v[2], v[3]); raw.z = pack_h2(v[4], v[5]); raw.w = pack_h2(v[6], v[7]);
+          raw_lo = pack_lo8(v, raw);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(ca[k], v[k], cb[k]));
+        packed.x = pack_h2(v[0], v[1]); packed.y = pack_h2(v[2], v[3]); packed.z = pack_h2(v[4], v[5]); packed.w = pack_h2(v[6], v[7]);
+      }
+      *reinterpret_cast<uint4*>(d_n + (size_t)pp * 16) = packed;
+      if (RAW) {
+        *reinterpret_cast<uint4*>(d_r + (size_t)pp * 16) = raw;
+        *reinterpret_cast<uint4*>(d_rl + (size_t)pp * 16) = raw_lo;
+      }
+    }
   }
 }
 

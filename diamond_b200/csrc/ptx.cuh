@@ -36,19 +36,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Non-blocking probe of a phase (no suspend): used to look ONE step ahead so that the ~130-cycle latency of a blocking wait on
-// an already-completed phase (measured with the clock64 timeline) is off the issuing thread's critical path.
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Bounded wait: a protocol bug must surface as a launch error (trap), never as a hung GPU.  A failed try_wait suspends for
 // an implementation-defined time up to the 1 ms hint (observed: microseconds), so 2^20 failures is seconds to minutes on
 // one phase -- orders of magnitude beyond the longest legitimate wait of any kernel here.

@@ -33,7 +33,8 @@ for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("stats+
 
 print("==== summary (cycles, mean over tiles 1..5 of CTA 0)")
 for name, kw in (("plain", dict(out_gs=0)), ("stats", dict(out_gs=32)), ("resid", dict(out_gs=0, residual=x)), ("stats+resid", dict(out_gs=32, residual=x)),
-                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("noMMA(dbg2)", dict(out_gs=0, debug=8 | 2))):
+                 ("skip-stores(dbg8)", dict(out_gs=0, debug=8)), ("noMMA(dbg2)", dict(out_gs=0, debug=8 | 2)),
+                 ("aligned-taps(dbg16)", dict(out_gs=0, debug=8 | 16))):
     buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device=dev)
     for rep in range(2):
         buf.zero_()
