@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "imagined frames/sec (64x64, 3 denoise steps)"
 GFLOP_PER_FRAME = 18.266  # 3 x 6.0888 GFLOP denoiser forwards
+TRS = os.environ.get("DMD_CONV_TRS", "1") != "0"  # the executor's weight layout for 3x3 convs (tap-row-stacked unless switched off)
 
 
 def load_peaks():
@@ -200,7 +201,7 @@ def conv_roofline(dev, envs, peaks, peaks_src):
 
     g = torch.Generator().manual_seed(0)
     wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
-    wpk, cp = ops.pack_conv_weight(wt, 64)
+    wpk, cp = ops.pack_conv_weight(wt, 64, trs=TRS)
     bias = torch.zeros(64, device=dev)
     nset = 6  # rotating operand / output sets: 6 x (17 MB operand + 33.5 MB output) at 32 envs > 126 MB L2
     xs = [torch.randn(envs, 64, 64, 64, device=dev) for _ in range(nset)]
@@ -213,7 +214,7 @@ def conv_roofline(dev, envs, peaks, peaks_src):
 
     def launch(i):
         k = i % nset
-        ops.conv2d_operand(opnd[k], None, 64, 0, envs, 64, 64, wpk, 64, cp, bias=bias, out_gs=32, out=outs[k], ostats=ost[k])
+        ops.conv2d_operand(opnd[k], None, 64, 0, envs, 64, 64, wpk, 64, cp, bias=bias, out_gs=32, out=outs[k], ostats=ost[k], trs=TRS)
 
     def launch_prep(i):
         k = i % nset
@@ -248,7 +249,7 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     traffic, traffic_src = conv_traffic_from_profile()
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<64> 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
+    return {"bound": "tensor", "kernel": ("conv_tc_kernel<256,3> (tap-row-stacked: 3 MMAs of N=192 per slab)" if TRS else "conv_tc_kernel<64,0> (tap-major: 9 MMAs of N=64 per slab)") + " 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
             "prep_us_per_launch": ms_prep * 1e3,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,

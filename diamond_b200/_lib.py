@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ("src0", _vp), ("src1", _vp), ("C0", _i), ("C1", _i), ("B", _i), ("H", _i), ("W", _i), ("taps", _i), ("stride", _i),
         ("wpk", _vp), ("bias", _vp), ("Cout", _i), ("CoutPad", _i),
         ("residual", _vp), ("out", _vp), ("out_stats", _vp), ("out_gs", _i), ("debug", _i), ("debug_buf", _vp),
-        ("precise", _i), ("src0_lo", _vp), ("src1_lo", _vp),
+        ("precise", _i), ("wpk_layout", _i), ("src0_lo", _vp), ("src1_lo", _vp),
         ("xsrc0", _vp), ("xsrc1", _vp), ("xsrc0_lo", _vp), ("xsrc1_lo", _vp), ("xC0", _i), ("xC1", _i), ("wpk_x", _vp), ("bias_x", _vp),
     ]
 

@@ -160,7 +160,11 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   const Plc g = plc_geometry(d->B, d->H, d->W);
   p->PW = g.PW; p->PH = g.PH; p->Q = g.Q; p->G = g.G; p->plane_bytes = (unsigned long long)g.Qalloc * 16;
   DMD_CHECK((long long)g.Q * (g.PW > g.PH ? g.PW : g.PH) < (1ll << 32), "conv: problem too large for 32-bit position math");
-  const int halo = d->taps == 9 ? g.PW + 1 : 0;
+  // tap-row-stacked mode (TrsEpilogue, conv_tc.cuh): weights packed with dmd_pack_conv_weight(precise = 3)
+  p->trs = d->wpk_layout == 1 ? 1 : 0;
+  if (p->trs) DMD_CHECK(d->taps == 9 && !d->precise && 3 * d->CoutPad <= 256, "conv: row-stacked weights need a 3x3, non-split conv with CoutPad <= 80");
+  p->tile_stride = p->trs ? 126 : kTileM;
+  const int halo = p->trs ? g.PW : (d->taps == 9 ? g.PW + 1 : 0);
   p->P = kTileM + 2 * halo; p->Palloc = p->P | 1;
   if (tune_int("DMD_CONV_PALLOC8", 0)) p->Palloc = round_up(p->P, 8);   // experiment: 128-byte aligned slab / chunk bases
   if (d->out_stats) {
@@ -171,20 +175,21 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
     DMD_CHECK(d->Cout % d->out_gs == 0 && d->Cout / d->out_gs <= kMaxOutGroups, "conv: bad output groups");
   }
   p->dPW.init(g.PW); p->dPH.init(g.PH);
-  p->num_tiles = (g.Q + kTileM - 1) / kTileM;
+  p->num_tiles = (g.Q + p->tile_stride - 1) / p->tile_stride;
   // slab ring: everything that fits next to the resident weights, at most four tiles' worth.  Two epilogue groups (each with
   // its own staging tile) when the ring still gets >= 4 slabs and a CTA sees at least two tiles; else one group.
   const int kslabs = (p->Cin + p->Cextra) / 16;
   const uint32_t w_bytes = conv_weight_bytes(p->taps, p->Cin, p->Cextra, p->CoutPad);
   // epilogue organisation: direct (0) unless switched off (DMD_CONV_EPI=0) or a warp's columns would span several GroupNorm groups
   const bool direct = tune_int("DMD_CONV_EPI", 1) != 0 && (!d->out_stats || d->CoutPad <= 64);
-  int groups = direct ? 0 : (tune_int("DMD_CONV_GROUPS", 2) >= 2 ? 2 : 1);
+  if (p->trs) DMD_CHECK(!d->out_stats || d->CoutPad <= 64, "conv: row-stacked mode computes statistics for CoutPad <= 64");
+  int groups = p->trs ? 3 : (direct ? 0 : (tune_int("DMD_CONV_GROUPS", 2) >= 2 ? 2 : 1));
   int stages = 0;
   for (;; groups = 1) {
     const ConvSmemLayout L0 = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, 0, groups);
     const long long budget = 227ll * 1024 - (long long)L0.total;
     stages = budget > 0 ? (int)(budget / (long long)L0.slab_bytes) : 0;
-    if (groups <= 1 || stages >= (kslabs < 4 ? kslabs + 1 : 4)) break;
+    if (groups <= 1 || groups == 3 || stages >= (kslabs < 4 ? kslabs + 1 : 4)) break;
   }
   if (stages > 4 * kslabs) stages = 4 * kslabs;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -194,6 +199,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   p->egroups = groups;
   *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages, groups).total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
+  if (p->trs) *tmem_cols = 3 * d->CoutPad <= 64 ? 64 : (3 * d->CoutPad <= 128 ? 128 : 256);   // accumulator = three column blocks
   return 0;
 }
 
@@ -213,6 +219,9 @@ static int init_kernels() {
   if (it == states.end()) {
     DevState st;
     DMD_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DMD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -362,7 +371,20 @@ extern "C" int dmd_prep_act(const dmd_prep_desc* d, void* stream) {
   return prep_launch(p, nsrc, (cudaStream_t)stream);
 }
 
+static int conv_launch_trs(const ConvParams& p0, size_t smem, int tmem_cols, cudaStream_t st) {
+  if (init_kernels()) return 1;
+  const int grid = p0.num_tiles < g_num_sms ? p0.num_tiles : g_num_sms;
+  ConvParams p = p0;
+  p.ktrace = kt_slot("conv3x3rs", p.num_tiles, (p.Cin + p.Cextra) * 1000 + p.W);
+  switch (tmem_cols) {
+    case 64: return launch_pdl(conv_tc_kernel<64, 3>, dim3(grid), dim3(kConvThreads), smem, st, p);
+    case 128: return launch_pdl(conv_tc_kernel<128, 3>, dim3(grid), dim3(kConvThreads), smem, st, p);
+    default: return launch_pdl(conv_tc_kernel<256, 3>, dim3(grid), dim3(kConvThreads), smem, st, p);
+  }
+}
+
 static int conv_launch(const ConvParams& p, size_t smem, int tmem_cols, cudaStream_t st) {
+  if (p.trs) return conv_launch_trs(p, smem, tmem_cols, st);
   switch (tmem_cols) {
     case 32: return conv_launch_t<32>(p, smem, st);
     case 64: return conv_launch_t<64>(p, smem, st);
@@ -479,7 +501,14 @@ extern "C" int dmd_pack_conv_weight_dgrad(const float* w, void* wpk, int CoutF, 
 extern "C" int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int CinReal, int Cin, int taps,
                                     int c0_real, int c0_store, int precise, void* stream) {
   DMD_CHECK(w && wpk, "pack: null pointer");
-  DMD_CHECK(precise >= 0 && precise <= 2, "pack: precise must be 0, 1 (split [W_hi | W_hi | W_lo]) or 2 (low parts only)");
+  if (precise == 3) {   // tap-row-stacked layout [dy][Cin/8][3 * CoutPad][8]: column dx * CoutPad + co of kernel row dy
+    DMD_CHECK(taps == 9, "pack: the row-stacked layout is for 3x3 kernels");
+    const int total3 = 9 * Cin * CoutPad;
+    pack_conv_weight_trs_kernel<<<(total3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, c0_real, c0_store);
+    DMD_LAUNCH_OK();
+    return 0;
+  }
+  DMD_CHECK(precise >= 0 && precise <= 2, "pack: precise must be 0, 1 (split [W_hi | W_hi | W_lo]), 2 (low parts only) or 3 (row-stacked)");
   const int total = taps * Cin * CoutPad * (precise == 1 ? 3 : 1);
   pack_conv_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpk, Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store, precise);
   DMD_LAUNCH_OK();
@@ -507,7 +536,7 @@ static int attn_launch(const AttnParams& p, int B, cudaStream_t st) {
   if (tune_int("DMD_ATTN_CLUSTER", 1) != 0 && p.gs % (p.C / 4) == 0) {
     // four CTAs per image (thread-block cluster), distributed shared memory for the head outputs
     const int CH = p.C / 4;
-    const size_t csmem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * CH + 4) + (size_t)p.L * CH);
+    const size_t csmem = sizeof(float) * ((size_t)p.L * (p.C + 1) * 2 + (size_t)p.L * (3 * CH + 4) + (size_t)p.L * CH + (size_t)4 * CH * p.C);
     if (p.C == 64) attn_cluster_kernel<64><<<4 * B, kAttnCThreads, csmem, st>>>(pt);
     else attn_cluster_kernel<32><<<4 * B, kAttnCThreads, csmem, st>>>(pt);
     DMD_LAUNCH_OK();
@@ -564,6 +593,7 @@ struct ConvW {          // one nn.Conv2d
   int w_idx, b_idx;     // indices into the state_dict pointer list
   int Cout, CoutPad, CinReal, Cin, taps, c0_real, c0_store;
   int precise = 0;      // split-fp16: K = 3 * Cin
+  int trs = 0;          // forward weights in the tap-row-stacked layout (3x3, non-split)
   int three_pass = 0;   // split-fp16 as three launches (A_hi W_hi, A_lo W_hi, A_hi W_lo) when 3 * Cin weights exceed shared memory
   size_t pk_off;        // byte offset into the packed-weight buffer
   size_t pk_lo_off = 0; // three_pass: the low-part pack
@@ -699,6 +729,7 @@ struct Walker {  // assigns state_dict indices in module registration order and 
     ConvW c; c.w_idx = next((long long)cout * cin_real * taps); c.b_idx = next(cout);
     c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
     c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16); c.precise = precise;
+    c.trs = (taps == 9 && !precise && 3 * c.CoutPad <= 256 && tune_int("DMD_CONV_TRS", 1) != 0) ? 1 : 0;
     c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2 * (precise ? 3 : 1); pk = (pk + 255) & ~(size_t)255;
     if (dgrad) {
       c.nsrcT = c1 ? 2 : 1;
@@ -848,7 +879,7 @@ struct PlanBuilder {
 
   // the conv with its input transform inside the kernel (conv_fused.cuh); false: not applicable (the caller materialises)
   bool try_fused(const ConvW& cw, Operand& in, int stride, const Tens* resid, Tens& out, bool out_stats, const ConvW* xproj, Operand* xin) {
-    if (!in.lazy || cw.precise || (xproj && !(xin && xin->lazy))) return false;
+    if (!in.lazy || cw.precise || cw.trs || (xproj && !(xin && xin->lazy))) return false;   // (the fused kernel reads tap-major weights)
     if (in.mode != 0 && (in.a.C / in.a.gs > 4 || (in.has_b && in.b.C / in.b.gs > 4))) return false;   // coefficient table: 4 groups per source
     Op op; op.kind = OP_FUSED;
     FusedParams& f = op.fused; memset(&f, 0, sizeof(f));
@@ -911,7 +942,7 @@ struct PlanBuilder {
       d.wpk_x = h->packed ? h->packed + xproj->pk_off : (const void*)1; d.bias_x = P(xproj->b_idx);
     }
     d.src0 = raw ? in.r0 : in.n0; d.src1 = in.C1 ? (raw ? in.r1 : in.n1) : nullptr;
-    d.precise = cw.precise;
+    d.precise = cw.precise; d.wpk_layout = cw.trs;
     if (cw.precise) { d.src0_lo = raw ? in.rl0 : in.nl0; d.src1_lo = in.C1 ? in.rl1 : nullptr; }
     d.C0 = in.C0; d.C1 = in.C1; d.B = pl->B; d.H = in.H; d.W = in.W; d.taps = cw.taps; d.stride = stride;
     d.wpk = h->packed ? h->packed + cw.pk_off : (const void*)1; d.bias = P(cw.b_idx);
@@ -1393,7 +1424,7 @@ extern "C" int dmd_denoiser_num_tensors(const dmd_denoiser* h) { return h->n_ten
 extern "C" size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h) { return h->packed_bytes; }
 
 static int pack_one(dmd_denoiser* h, const ConvW& c, cudaStream_t st) {
-  if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.precise, st)) return 1;
+  if (dmd_pack_conv_weight(h->ptrs[c.w_idx], h->packed + c.pk_off, c.Cout, c.CoutPad, c.CinReal, c.Cin, c.taps, c.c0_real, c.c0_store, c.trs ? 3 : c.precise, st)) return 1;
   for (int k = 0; k < c.nsrcT; ++k)  // backward-data packs (transposed, flipped), one per concat source
     if (dmd_pack_conv_weight_dgrad(h->ptrs[c.w_idx], h->packed + c.pkT_off[k], c.Cout, c.CinReal, c.srcOff[k], c.srcC[k], c.taps, st)) return 1;
   return 0;

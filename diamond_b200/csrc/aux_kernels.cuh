@@ -388,11 +388,24 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kAttnCThreads) attn_
   float* qkv = xs + L * XP;         // [L][QP]  local q, k, v
   float* ys = qkv + L * QP;         // [L][CH]  local y (read by the other ranks)
   float* ya = ys + L * CH;          // [L][XP]  all channels of y
+  float* wq = ya + L * XP;          // [Q3][C]  this rank's rows of the in-projection (staged once, coalesced: the per-thread
+  float* wo = wq + Q3 * C;          // [CH][C]  ... and of the out-projection     broadcast reads then come from shared memory)
   __shared__ float smr[8][2];
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();
   const int n = blockIdx.x >> 2, tid = threadIdx.x;
   if (blockIdx.x == 0 && tid == 0) ktrace_stamp(p.ktrace);
+  // weights first: they do not depend on the previous kernel's output, and every later read is a shared-memory broadcast instead
+  // of an L2 round trip per (thread, row, 4 input channels)
+  for (int i = tid; i < Q3 * (C / 4); i += kAttnCThreads) {
+    const int j = i / (C / 4), c4 = i - j * (C / 4);
+    const int part = j / CH, cc = j - part * CH;
+    reinterpret_cast<float4*>(wq)[i] = __ldg(reinterpret_cast<const float4*>(p.wqkv + (size_t)(part * C + r * CH + cc) * C) + c4);
+  }
+  for (int i = tid; i < CH * (C / 4); i += kAttnCThreads) {
+    const int j = i / (C / 4), c4 = i - j * (C / 4);
+    reinterpret_cast<float4*>(wo)[i] = __ldg(reinterpret_cast<const float4*>(p.wout + (size_t)(r * CH + j) * C) + c4);
+  }
   const int G = C / p.gs;
   if (tid < G) {
     const double cnt = (double)L * p.gs;
@@ -427,7 +440,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kAttnCThreads) attn_
       const float x0 = xs[l * XP + 4 * c4], x1 = xs[l * XP + 4 * c4 + 1], x2 = xs[l * XP + 4 * c4 + 2], x3 = xs[l * XP + 4 * c4 + 3];
 #pragma unroll
       for (int i = 0; i < NO; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wqkv + (size_t)row[i] * C) + c4);
+        const float4 w = reinterpret_cast<const float4*>(wq + (og * NO + i) * C)[c4];
         acc[i] = fmaf(w.x, x0, acc[i]); acc[i] = fmaf(w.y, x1, acc[i]);
         acc[i] = fmaf(w.z, x2, acc[i]); acc[i] = fmaf(w.w, x3, acc[i]);
       }
@@ -504,7 +517,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kAttnCThreads) attn_
       const float y0 = ya[l * XP + 4 * c4], y1 = ya[l * XP + 4 * c4 + 1], y2 = ya[l * XP + 4 * c4 + 2], y3 = ya[l * XP + 4 * c4 + 3];
 #pragma unroll
       for (int i = 0; i < NO2; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.wout + (size_t)(oc0 + i) * C) + c4);
+        const float4 w = reinterpret_cast<const float4*>(wo + (og * NO2 + i) * C)[c4];
         acc[i] = fmaf(w.x, y0, acc[i]); acc[i] = fmaf(w.y, y1, acc[i]);
         acc[i] = fmaf(w.z, y2, acc[i]); acc[i] = fmaf(w.w, y3, acc[i]);
       }
@@ -602,6 +615,28 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
     if (co < Cout && cr >= 0 && cr < CinReal) v = w[((size_t)co * CinReal + cr) * taps + t];
     const __half hi = __float2half_rn(v);
     wpk[i] = (precise != 2 && seg < 2) ? hi : __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// Tap-row-stacked packing (TrsEpilogue, conv_tc.cuh): [dy 3][Cin/8][3 * CoutPad][8] fp16, column n = dx * CoutPad + co of kernel
+// row dy holds W[co][ci][dy][dx]; channel mapping (c0_real / c0_store / concat) as in pack_conv_weight_kernel.
+__global__ void pack_conv_weight_trs_kernel(const float* __restrict__ w, __half* __restrict__ wpk, int Cout, int CoutPad, int CinReal,
+                                            int Cin, int c0_real, int c0_store) {
+  const int N3 = 3 * CoutPad;
+  const int total = 3 * Cin * N3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    const int n = (i >> 3) % N3;
+    const int j = (i >> 3) / N3 % (Cin >> 3);
+    const int dy = (i >> 3) / N3 / (Cin >> 3);
+    const int dx = n / CoutPad, co = n - dx * CoutPad;
+    const int ci = j * 8 + e;
+    int cr = -1;
+    if (ci < c0_store) cr = ci < c0_real ? ci : -1;
+    else cr = c0_real + (ci - c0_store);
+    float v = 0.f;
+    if (co < Cout && cr >= 0 && cr < CinReal) v = w[((size_t)co * CinReal + cr) * 9 + dy * 3 + dx];
+    wpk[i] = __float2half_rn(v);
   }
 }
 

@@ -60,7 +60,7 @@ struct Plc {
 __host__ __device__ inline Plc plc_geometry(int B, int H, int W) {
   Plc g;
   g.PW = W + 1; g.PH = H + 1; g.Q = B * g.PH * g.PW; g.G = g.PW + 1;
-  g.Qalloc = g.G + ((g.Q + kTileM - 1) / kTileM) * kTileM + g.PW + 1;
+  g.Qalloc = g.G + ((g.Q + kTileM - 1) / kTileM) * kTileM + kTileM + g.PW + 1;   // + one tile: 126-row (tap-row-stacked) tiling reads further
   return g;
 }
 
@@ -90,6 +90,8 @@ struct ConvParams {
   unsigned long long plane_bytes;  // bytes of one chunk plane (same geometry for both sources)
   int P, Palloc;        // halo positions, odd allocation pitch
   int num_tiles, stages;
+  int trs;              // tap-row-stacked mode (see TrsEpilogue): weights [dy][Cin/8][3*CoutPad][8], tiles advance by 126 positions
+  int tile_stride;      // 128, or 126 in trs mode
   int egroups;          // epilogue groups: 1 = eight warps share every tile; 2 = two groups of four warps take alternate tiles
   FastDiv dPW, dPH;
   int dbg;
@@ -113,6 +115,15 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int
   L.sstat_off = L.rowinfo_off + (uint32_t)groups * kTileM * 8;   // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
   L.stage_off = (L.sstat_off + (groups ? kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 : 0) + 127u) & ~127u;
+  if (groups == 3) {   // tap-row-stacked: no staging, a boundary-row exchange buffer [parity 2][kind 2][quarter 4][128] floats instead
+    L.rowinfo_off = L.sstat_off = L.bias_off + 128 * 4;
+    L.stage_off = L.rowinfo_off;
+    L.w_off = (L.stage_off + 2u * 2u * 4u * 128u * 4u + 127u) & ~127u;
+    L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
+    L.slab_bytes = 2u * Palloc * 16;
+    L.total = L.a_off + (uint32_t)stages * L.slab_bytes + 16;
+    return L;
+  }
   L.w_off = (L.stage_off + (uint32_t)groups * kTileM * L.stage_pitch + 127u) & ~127u;   // one staging tile per group
   L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
   L.slab_bytes = 2u * Palloc * 16;
@@ -296,6 +307,218 @@ struct DirectEpilogue {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tap-row-stacked (TRS) 3x3 convolution.  Measured (clock64 timeline, scripts/timeline_conv.py): a tcgen05.mma M128 x N64 x K16
+// with both operands in shared memory takes ~72 cycles on this part independent of operand alignment -- the 4 KB A-operand read
+// per instruction is the bound (N = 64 gives the tensor pipe 32 cycles of work) -- so nine taps x four slabs cost ~2.6 k cycles
+// per 128-row tile.  The three taps of one kernel ROW (dy fixed, dx = -1, 0, +1) read windows that differ by ONE position, so they
+// can share one A read if the dx shift is moved to the OUTPUT side:
+//     D[r][dx*Cout + co] = sum_c X[w0 + r + dy*PW][c] * W[dy][dx][c][co]        one MMA, N = 3 * Cout, per (slab, dy)
+//     out[w0 + m][co]    = D[m - 1][co] + D[m][Cout + co] + D[m + 1][2*Cout + co]      m = 1 .. 126
+// Three MMAs of N = 192 per slab instead of nine of N = 64: a third of the A reads, the tensor pipe becomes the bound.  The price:
+// a tile yields 126 outputs from 128 window rows (tiles advance by 126 positions), the accumulator is 3x wider (2 x 192 TMEM
+// columns), and the epilogue adds three row-shifted accumulator blocks.  With the 16-lane x 256-bit TMEM load pattern the rows
+// m - 1 / m + 1 of a thread's four rows live four lanes away (one shuffle each) except at the edges of a warp's 32-row quarter,
+// which are exchanged through a 4 KB shared-memory buffer (one named barrier per 16-column chunk).
+template <int kAccCols>
+struct TrsEpilogue {
+  int quarter, blk_begin, blk_end, g, lc, G, my_grp, lane;
+  bool vec2;
+  float s0, s1, s2, ss0, ss1, ss2;
+  int n_cur;
+
+  __device__ __forceinline__ void init(const ConvParams& p, int warp, int lane_) {
+    lane = lane_;
+    const int ew = warp - 2;
+    quarter = warp & 3;
+    const int half = ew >> 2;
+    const int nblk = p.CoutPad >> 3;
+    const int hb = nblk >> 1;                  // CoutPad is a multiple of 16: equal halves (every warp runs the same number of chunks)
+    blk_begin = half ? hb : 0; blk_end = half ? nblk : hb;
+    g = lane >> 2; lc = (lane & 3) * 2;
+    vec2 = (p.Cout & 1) == 0;
+    G = p.ostats ? p.Cout / p.ogs : 1;
+    my_grp = p.ostats ? min(G - 1, (blk_begin * 8) / p.ogs) : 0;
+    s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+    n_cur = -1;
+  }
+
+  __device__ __forceinline__ void flush_stats(const ConvParams& p, int img0, bool multi) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+      ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+      if (multi) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        ss2 += __shfl_xor_sync(0xffffffffu, ss2, m);
+      }
+    }
+    if (lane == 0) {
+      double* dst = p.ostats + ((size_t)img0 * G + my_grp) * 2;
+      if (img0 < p.B && (s0 != 0.f || ss0 != 0.f)) { atomicAdd(dst, (double)s0); atomicAdd(dst + 1, (double)ss0); }
+      if (multi) {
+        if (img0 + 1 < p.B && (s1 != 0.f || ss1 != 0.f)) { atomicAdd(dst + (size_t)G * 2, (double)s1); atomicAdd(dst + (size_t)G * 2 + 1, (double)ss1); }
+        if (img0 + 2 < p.B && (s2 != 0.f || ss2 != 0.f)) { atomicAdd(dst + (size_t)G * 4, (double)s2); atomicAdd(dst + (size_t)G * 4 + 1, (double)ss2); }
+      }
+    }
+    s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+  }
+
+  // tile index ti: window rows r = 0..127 are positions w0 + r, w0 = 126 * ti - 1; outputs are rows 1..126.
+  // bnd: shared exchange buffer [parity 2][kind 2 (0: row 31 of D_-1, 1: row 0 of D_+1)][quarter 4][128] floats
+  __device__ __forceinline__ void tile(const ConvParams& p, const float* sbias, float* bnd, uint32_t tmem_acc, int ti, uint64_t* tfull,
+                                       uint32_t parity, uint64_t* tempty) {
+    const int w0 = ti * 126 - 1;
+    const int q_first = w0 + 1;
+    const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q_first));
+    const int q_last = min(q_first + 126, p.Q) - 1;
+    const bool single_image = (int)p.dPH.div(p.dPW.div((uint32_t)q_last)) == n_lo;
+    if (n_cur >= 0 && (!single_image || n_lo != n_cur)) { flush_stats(p, n_cur, false); n_cur = -1; }
+    // the four window rows of this thread: m = quarter*32 + 8*j + g, j = 0..3
+    int opix[4], slot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = quarter * 32 + 8 * j + g;
+      const int q = w0 + m;
+      opix[j] = -1; slot[j] = 0;
+      if (m >= 1 && m <= 126 && q < p.Q) {
+        const uint32_t R = p.dPW.div((uint32_t)q);
+        const int x = q - (int)R * p.PW;
+        const int n = (int)p.dPH.div(R);
+        const int y = (int)R - n * p.PH;
+        bool valid = (x < p.W) && (y < p.H);
+        int yo = y, xo = x, Ho = p.H, Wo = p.W;
+        if (p.stride == 2) {
+          valid = valid && ((x & 1) == 0) && ((y & 1) == 0);
+          yo = y >> 1; xo = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+        }
+        if (valid) { opix[j] = (n * Ho + yo) * Wo + xo; slot[j] = n - n_lo; }
+      }
+    }
+    float* bup = bnd + (size_t)((ti & 1) * 2 + 0) * 4 * 128;    // [quarter][col]: row 31 of the D_-1 block
+    float* bdn = bnd + (size_t)((ti & 1) * 2 + 1) * 4 * 128;    //                 row 0 of the D_+1 block
+    bool waited = false;
+    auto chunk = [&](auto nbc, auto vecc, int blk) {
+      constexpr int NB = decltype(nbc)::value;
+      constexpr bool VEC = decltype(vecc)::value;
+      const int col0 = blk * 8 + lc;
+      float2 rr[4][NB];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          rr[j][k] = make_float2(0.f, 0.f);
+          const int col = col0 + 8 * k;
+          if (p.resid != nullptr && opix[j] >= 0 && col < p.Cout) {
+            const float* rp = p.resid + (size_t)opix[j] * p.Cout + col;
+            if (VEC) rr[j][k] = __ldg(reinterpret_cast<const float2*>(rp));
+            else { rr[j][k].x = __ldg(rp); if (col + 1 < p.Cout) rr[j][k].y = __ldg(rp + 1); }
+          }
+        }
+      if (!waited) {
+        mbar_wait(tfull, parity);
+        tc_fence_after_sync();
+        waited = true;
+      }
+      uint32_t rm[8 * NB], rz[8 * NB], rp_[8 * NB];   // D_-1, D_0, D_+1 blocks: columns dx * CoutPad + blk*8 ...
+      const uint32_t ta = tmem_acc + (uint32_t)(blk * 8) + ((uint32_t)(quarter * 32) << 16);
+      tmem_ld_16x256b_pair<NB>(ta, ta + (16u << 16), rm);
+      tmem_ld_16x256b_pair<NB>(ta + (uint32_t)p.CoutPad, ta + (uint32_t)p.CoutPad + (16u << 16), rz);
+      tmem_ld_16x256b_pair<NB>(ta + 2u * (uint32_t)p.CoutPad, ta + 2u * (uint32_t)p.CoutPad + (16u << 16), rp_);
+      if (blk + NB >= blk_end) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0 && tempty != nullptr) mbar_arrive(tempty);
+      }
+      // ---- edge rows of this warp's quarter for the neighbouring quarters
+      if (g == 7) {   // window row 31 of the quarter (j = 3 -> register block h = 1, s = 1)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          bup[quarter * 128 + col0 + 8 * k] = __uint_as_float(rm[4 * NB + 4 * k + 2]);
+          bup[quarter * 128 + col0 + 8 * k + 1] = __uint_as_float(rm[4 * NB + 4 * k + 3]);
+        }
+      }
+      if (g == 0) {   // window row 0 of the quarter (j = 0 -> h = 0, s = 0)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          bdn[quarter * 128 + col0 + 8 * k] = __uint_as_float(rp_[4 * k]);
+          bdn[quarter * 128 + col0 + 8 * k + 1] = __uint_as_float(rp_[4 * k + 1]);
+        }
+      }
+      named_bar_sync(1, kEpiThreads);
+      const int src_up = (lane - 4) & 31, src_dn = (lane + 4) & 31;
+      float2 bv[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) bv[k] = (col0 + 8 * k < p.Cout) ? *reinterpret_cast<const float2*>(sbias + col0 + 8 * k) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          // register of window row 8*j + g: index (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1) + e
+          float tm[4], tp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1) + e;
+            tm[j] = __shfl_sync(0xffffffffu, __uint_as_float(rm[idx]), src_up);    // D_-1 at the lane four below (row - 1 when g >= 1)
+            tp[j] = __shfl_sync(0xffffffffu, __uint_as_float(rp_[idx]), src_dn);   // D_+1 at the lane four above (row + 1 when g <= 6)
+          }
+          const int col = col0 + 8 * k + e;
+          const float e_up = (quarter > 0) ? bup[(quarter - 1) * 128 + col] : 0.f;   // row -1 of this quarter = row 31 of the previous one
+          const float e_dn = (quarter < 3) ? bdn[(quarter + 1) * 128 + col] : 0.f;   // row 32 = row 0 of the next one
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1) + e;
+            const float up = (g >= 1) ? tm[j] : (j >= 1 ? tm[j >= 1 ? j - 1 : 0] : e_up);
+            const float dn = (g <= 6) ? tp[j] : (j <= 2 ? tp[j <= 2 ? j + 1 : 3] : e_dn);
+            const float o = (up + __uint_as_float(rz[idx])) + dn + (e ? bv[k].y : bv[k].x) + (e ? rr[j][k].y : rr[j][k].x);
+            rz[idx] = __float_as_uint(o);      // the output value replaces the centre block register
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (opix[j] >= 0) {
+          float* op = p.out + (size_t)opix[j] * p.Cout + col0;
+          float sps = 0.f, spss = 0.f;
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            if (col0 + 8 * k < p.Cout) {
+              const int idx = (j >> 1) * 4 * NB + 4 * k + 2 * (j & 1);
+              const float ox = __uint_as_float(rz[idx]), oy = __uint_as_float(rz[idx + 1]);
+              if (VEC) *reinterpret_cast<float2*>(op + 8 * k) = make_float2(ox, oy);
+              else { op[8 * k] = ox; if (col0 + 8 * k + 1 < p.Cout) op[8 * k + 1] = oy; }
+              sps += ox + ((VEC || col0 + 8 * k + 1 < p.Cout) ? oy : 0.f);
+              spss = fmaf(ox, ox, spss); if (VEC || col0 + 8 * k + 1 < p.Cout) spss = fmaf(oy, oy, spss);
+            }
+          }
+          if (p.ostats != nullptr) {
+            const int sl = single_image ? 0 : slot[j];
+            s0 += (sl == 0) ? sps : 0.f;  ss0 += (sl == 0) ? spss : 0.f;
+            s1 += (sl == 1) ? sps : 0.f;  ss1 += (sl == 1) ? spss : 0.f;
+            s2 += (sl == 2) ? sps : 0.f;  ss2 += (sl == 2) ? spss : 0.f;
+          }
+        }
+      }
+    };
+    for (int blk = blk_begin; blk < blk_end;) {
+      const int rem = blk_end - blk;
+      if (!vec2) { chunk(std::integral_constant<int, 1>{}, std::false_type{}, blk); blk += 1; }
+      else if (rem >= 2) { chunk(std::integral_constant<int, 2>{}, std::true_type{}, blk); blk += 2; }
+      else { chunk(std::integral_constant<int, 1>{}, std::true_type{}, blk); blk += 1; }
+    }
+    if (p.ostats != nullptr) {
+      if (single_image) n_cur = n_lo;
+      else { flush_stats(p, n_lo, true); n_cur = -1; }
+    }
+  }
+
+  __device__ __forceinline__ void finish(const ConvParams& p) {
+    if (n_cur >= 0) flush_stats(p, n_cur, false);
+  }
+};
+
 // kAccCols: TMEM columns per accumulator (>= CoutPad); two accumulators are allocated.
 // kGroups : epilogue organisation.  0: DIRECT -- the eight warps read the accumulator with the 16-lane x 256-bit TMEM pattern, whose
 //           register layout puts 32 contiguous bytes of an output row into four neighbouring threads, and store (+bias, +residual)
@@ -322,7 +545,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int halo = (p.taps == 9) ? (p.PW + 1) : 0;
+  // halo positions in front of the tile's first window row (row-stacked mode: one image row; the dx shift lives on the output side)
+  const int halo = p.trs ? p.PW : ((p.taps == 9) ? (p.PW + 1) : 0);
+  const int lead = p.trs ? 1 : 0;            // window rows in front of the first output row
   const int S = p.stages;
   const int main_slabs = p.Cin >> 4;
   const int kslabs = main_slabs + (p.Cextra >> 4);
@@ -337,7 +562,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kGroups == 0 ? kEpiWarps : kEpiWarps / (kGroups ? kGroups : 1)); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, (kGroups == 0 || kGroups == 3) ? kEpiWarps : kEpiWarps / kGroups); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     const uint32_t extra_bytes = (uint32_t)p.Cextra * p.CoutPad * 2;
@@ -349,7 +574,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_slot);
   for (int i = tid; i < 128; i += blockDim.x)
     sbias[i] = ((p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f) + ((p.bias_extra != nullptr && i < p.Cout) ? __ldg(p.bias_extra + i) : 0.f);
-  if (kGroups != 0)
+  if (kGroups == 1 || kGroups == 2)
     for (int i = tid; i < kEpiWarps * kStatSlots * kMaxOutGroups * 2; i += blockDim.x) reinterpret_cast<float*>(smem + L.sstat_off)[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
@@ -365,7 +590,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         // first halo position of this tile inside a plane (guard G keeps it non-negative)
-        const size_t pos0 = (size_t)((tile_begin + it) * kTileM - halo + p.G) * 16;
+        const size_t pos0 = (size_t)((tile_begin + it) * p.tile_stride - lead - halo + p.G) * 16;
         int seg = 0, seg_ks = 0;  // current operand segment and slab index inside it
         for (int ks = 0; ks < kslabs; ++ks) {
           DMD_TS(0, it, (ks & 3) * 3 + 0);
@@ -412,6 +637,50 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         shift[t] = (uint32_t)(halo + (nine ? (t / 3 - 1) * p.PW + (t % 3 - 1) : 0));
         b_tap[t] = (uint32_t)t * tap16;
       }
+      if constexpr (kGroups == 3) {
+        // ---- tap-row-stacked: per slab three MMAs (dy = -1, 0, +1) of N = 3 * CoutPad, A shifted by whole image rows only
+        const uint32_t idesc3 = umma_idesc_f16(kTileM, 3u * (uint32_t)p.CoutPad, 0, 0);
+        const uint32_t b3_lbo = 3u * (uint32_t)p.CoutPad * 16;
+        const uint32_t b3_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (((b3_lbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t row16 = ((uint32_t)p.Cin * 3u * p.CoutPad * 2) >> 4;   // one kernel row (three taps) of weights, /16
+        const uint32_t k3step16 = (2u * b3_lbo) >> 4;
+        const uint32_t pw = (uint32_t)p.PW;
+        uint32_t stage = 0, phase = 0, a_lo = a_lo0;
+        uint32_t tph0 = 1u, tph1 = 1u;
+        for (int it = 0; it < my_tiles; ++it) {
+          const int b = it & 1;
+          mbar_wait(tempty + b, b ? tph1 : tph0);
+          if (b) tph1 ^= 1u; else tph0 ^= 1u;
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
+          uint32_t b_lo = b3_lo0;
+          for (int ks = 0; ks < kslabs; ++ks) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after_sync();
+            if (elect_one_sync()) {
+              if (ks >= main_slabs) {
+                // fused 1x1 projection: centre tap, N = CoutPad, accumulated into the dx = 0 column block
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + pw);
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
+                umma_f16(d_tmem + (uint32_t)p.CoutPad, ad, bd, idesc, 1u);
+              } else {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                  const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)dy * pw);
+                  const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)dy * row16);
+                  umma_f16(d_tmem, ad, bd, idesc3, (ks | dy) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(empty + stage);
+              if (ks == kslabs - 1) umma_commit(tfull + b);
+            }
+            __syncwarp();
+            b_lo += k3step16;
+            a_lo += slab16;
+            if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+          }
+        }
+      } else {
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
       uint32_t tph0 = 1u, tph1 = 1u;  // parity to wait on for tempty[b]: first use passes immediately
       for (int it = 0; it < my_tiles; ++it) {
@@ -459,11 +728,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         }
         DMD_TS(1, it, 14);
       }
+      }  // generic tap loop
     }
     __syncwarp();
   } else {
     // =========================================================================================== EPILOGUE (8 warps)
-    if constexpr (kGroups == 0) {
+    if constexpr (kGroups == 3) {
+      // ---- tap-row-stacked epilogue: three row-shifted accumulator blocks -> registers -> global (TrsEpilogue above)
+      TrsEpilogue<kAccCols> epi;
+      epi.init(p, warp, lane);
+      float* bnd = reinterpret_cast<float*>(smem + L.stage_off);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        epi.tile(p, sbias, bnd, tmem_base + (uint32_t)b * kAccCols, tile_begin + it, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b);
+      }
+      epi.finish(p);
+    } else if constexpr (kGroups == 0) {
       // ---- direct epilogue: TMEM (16 lanes x 256 bit pattern) -> registers -> (+bias, +residual) -> global (DirectEpilogue above)
       DirectEpilogue<kAccCols> epi;
       epi.init(p, warp, lane);

@@ -37,8 +37,9 @@ def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
 
 
 def pack_conv_weight(w: Tensor, cin_pad: int, c0_real: Optional[int] = None, c0_store: Optional[int] = None,
-                     precise: bool = False) -> Tuple[Tensor, int]:
-    """torch weight [Cout][Cin][k][k] -> fp16 operand [taps][cin_pad/8][CoutPad][8]; returns (packed, CoutPad)."""
+                     precise: bool = False, trs: bool = False) -> Tuple[Tensor, int]:
+    """torch weight [Cout][Cin][k][k] -> fp16 operand [taps][cin_pad/8][CoutPad][8]; returns (packed, CoutPad).
+    trs=True: the tap-row-stacked layout of 3x3 kernels (pass trs=True to the conv call as well)."""
     _cuda(w)
     cout, cin, kh, kw = w.shape
     taps = kh * kw
@@ -47,7 +48,7 @@ def pack_conv_weight(w: Tensor, cin_pad: int, c0_real: Optional[int] = None, c0_
     c0_store = c0_real if c0_store is None else c0_store
     out = torch.empty(taps * cin_pad * cout_pad * (3 if precise else 1), device=w.device, dtype=torch.float16)
     _lib.check(_lib.lib().dmd_pack_conv_weight(w.data_ptr(), out.data_ptr(), cout, cout_pad, cin, cin_pad, taps,
-                                              c0_real, c0_store, int(precise), _lib.current_stream()))
+                                              c0_real, c0_store, 3 if trs else int(precise), _lib.current_stream()))
     return out, cout_pad
 
 
@@ -96,7 +97,7 @@ def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h
                    cout_pad: int, taps: int = 9, *, bias: Optional[Tensor] = None, stride: int = 1,
                    residual: Optional[Tensor] = None, out_gs: int = 0, out: Optional[Tensor] = None,
                    ostats: Optional[Tensor] = None, debug: int = 0, debug_buf: Optional[Tensor] = None,
-                   lo0: Optional[Tensor] = None, lo1: Optional[Tensor] = None, xproj=None):
+                   lo0: Optional[Tensor] = None, lo1: Optional[Tensor] = None, xproj=None, trs: bool = False):
     """tcgen05 conv on already prepared PLC16 operand(s) (one kernel launch)."""
     _cuda(n0, n1, wpk, bias, residual)
     ho, wo = h // stride, w // stride
@@ -111,6 +112,7 @@ def conv2d_operand(n0: Tensor, n1: Optional[Tensor], c0: int, c1: int, b: int, h
     d.residual, d.out, d.out_stats, d.out_gs, d.debug = _lib.ptr(residual), out.data_ptr(), _lib.ptr(ostats), out_gs, debug
     d.debug_buf = _lib.ptr(debug_buf)
     d.precise, d.src0_lo, d.src1_lo = int(lo0 is not None), _lib.ptr(lo0), _lib.ptr(lo1)
+    d.wpk_layout = int(trs)
     if xproj is not None:  # fused split-fp16 1x1 projection: (hi0, hi1, lo0, lo1, C0, C1, wpk_x, bias_x)
         xh0, xh1, xl0, xl1, xc0, xc1, wpk_x, bias_x = xproj
         d.xsrc0, d.xsrc1, d.xsrc0_lo, d.xsrc1_lo = xh0.data_ptr(), _lib.ptr(xh1), xl0.data_ptr(), _lib.ptr(xl1)
@@ -125,7 +127,7 @@ def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: i
                  gs0: int = 0, gs1: int = 0, film: Optional[Tensor] = None, film_off: int = 0,
                  gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
                  residual: Optional[Tensor] = None, out_gs: int = 0, debug: int = 0, debug_buf: Optional[Tensor] = None,
-                 precise: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+                 precise: bool = False, trs: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
     """The reference's `conv(act(norm(cat(x, skip))))` on NHWC fp32 tensors: one prep launch + one tcgen05 conv launch.
     precise=True: split-fp16 operands (weights must be packed with precise=True)."""
     res = prep_act(src0, src1=src1, upsample=upsample, mode=prologue, silu=silu, stats0=stats0, stats1=stats1,
@@ -136,7 +138,7 @@ def conv2d_fprop(src0: Tensor, wpk: Tensor, cout: int, cout_pad: int, cin_pad: i
     if c0 + c1 != cin_pad:
         raise ValueError(f"operand channels {c0}+{c1} do not match the packed weights ({cin_pad})")
     return conv2d_operand(n0, n1, c0, c1, src0.shape[0], h, w, wpk, cout, cout_pad, taps, bias=bias, stride=stride,
-                          residual=residual, out_gs=out_gs, debug=debug, debug_buf=debug_buf, lo0=lo0, lo1=lo1)
+                          residual=residual, out_gs=out_gs, debug=debug, debug_buf=debug_buf, lo0=lo0, lo1=lo1, trs=trs)
 
 
 def attn_fwd(x: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, wqkv: Tensor, bqkv: Tensor, wout: Tensor,

@@ -47,7 +47,9 @@ int dmd_pack_conv_weight(const float* w, void* wpk, int Cout, int CoutPad, int C
                          int c0_real, int c0_store, int precise, void* stream);
 /* precise = 1: split-fp16 packing [W_hi | W_hi | W_lo] (3*Cin channels per tap) for dmd_conv_desc.precise convs: the
  * product is evaluated as A_hi W_hi + A_lo W_hi + A_hi W_lo on the tensor cores, i.e. to ~2^-22 instead of 2^-11.  Used
- * for the layers whose input is the raw residual stream (1x1 skip projections, conv_in) and for conv_out. */
+ * for the layers whose input is the raw residual stream (1x1 skip projections, conv_in) and for conv_out.
+ * precise = 3: the tap-row-stacked layout [dy][Cin/8][3*CoutPad][8] of 3x3 kernels (dmd_conv_desc.wpk_layout = 1): one
+ * tensor-core instruction per kernel ROW with N = 3*CoutPad, the dx shift applied on the output side (conv_tc.cuh). */
 
 /* Activation operand ("PLC16": padded-linear, chunk-major fp16; layout in diamond_b200/csrc/conv_tc.cuh).  One pass over
  * an NHWC fp32 tensor applies what the reference runs on a conv INPUT — GroupNorm (blocks.py:28) or AdaGroupNorm
@@ -100,6 +102,7 @@ typedef struct dmd_conv_desc {
   int debug;             /* bring-up only; 0 */
   void* debug_buf;       /* bring-up only; NULL */
   int precise;           /* 1: split-fp16 (needs src*_lo and weights packed with precise = 1) */
+  int wpk_layout;        /* 0: tap-major weights ; 1: tap-row-stacked (dmd_pack_conv_weight precise = 3; 3x3, non-split only) */
   const void* src0_lo;
   const void* src1_lo;
   /* Optional fused 1x1 projection accumulated into the same output: out += W_x . cat(x0, x1) + b_x  (the skip path
