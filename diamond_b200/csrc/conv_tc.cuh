@@ -369,7 +369,10 @@ struct TrsEpilogue {
   // tile index ti: window rows r = 0..127 are positions w0 + r, w0 = 126 * ti - 1; outputs are rows 1..126.
   // bnd: shared exchange buffer [parity 2][kind 2 (0: row 31 of D_-1, 1: row 0 of D_+1)][quarter 4][128] floats
   __device__ __forceinline__ void tile(const ConvParams& p, const float* sbias, float* bnd, uint32_t tmem_acc, int ti, uint64_t* tfull,
-                                       uint32_t parity, uint64_t* tempty) {
+                                       uint32_t parity, uint64_t* tempty, int it = 0) {
+    (void)it;
+    const bool ts = threadIdx.x == 64;   // timeline stamps (DMD_TIMELINE builds): first epilogue thread
+    (void)ts;
     const int w0 = ti * 126 - 1;
     const int q_first = w0 + 1;
     const int n_lo = (int)p.dPH.div(p.dPW.div((uint32_t)q_first));
@@ -418,7 +421,9 @@ struct TrsEpilogue {
           }
         }
       if (!waited) {
+        if (ts) DMD_TS(2, it, 0);
         mbar_wait(tfull, parity);
+        if (ts) DMD_TS(2, it, 1);
         tc_fence_after_sync();
         waited = true;
       }
@@ -447,7 +452,9 @@ struct TrsEpilogue {
           bdn[quarter * 128 + col0 + 8 * k + 1] = __uint_as_float(rp_[4 * k + 1]);
         }
       }
+      if (ts && blk == blk_begin) DMD_TS(2, it, 2);
       named_bar_sync(1, kEpiThreads);
+      if (ts && blk == blk_begin) DMD_TS(2, it, 8);
       const int src_up = (lane - 4) & 31, src_dn = (lane + 4) & 31;
       float2 bv[NB];
 #pragma unroll
@@ -512,6 +519,7 @@ struct TrsEpilogue {
       if (single_image) n_cur = n_lo;
       else { flush_stats(p, n_lo, true); n_cur = -1; }
     }
+    if (ts) DMD_TS(2, it, 3);
   }
 
   __device__ __forceinline__ void finish(const ConvParams& p) {
@@ -649,13 +657,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
         uint32_t tph0 = 1u, tph1 = 1u;
         for (int it = 0; it < my_tiles; ++it) {
           const int b = it & 1;
+          DMD_TS(1, it, 12);
           mbar_wait(tempty + b, b ? tph1 : tph0);
+          DMD_TS(1, it, 13);
           if (b) tph1 ^= 1u; else tph0 ^= 1u;
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)b * kAccCols;
           uint32_t b_lo = b3_lo0;
           for (int ks = 0; ks < kslabs; ++ks) {
+            DMD_TS(1, it, (ks & 3) * 3 + 0);
             mbar_wait(full + stage, phase);
+            DMD_TS(1, it, (ks & 3) * 3 + 1);
             tc_fence_after_sync();
             if (elect_one_sync()) {
               if (ks >= main_slabs) {
@@ -675,10 +687,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
               if (ks == kslabs - 1) umma_commit(tfull + b);
             }
             __syncwarp();
+            DMD_TS(1, it, (ks & 3) * 3 + 2);
             b_lo += k3step16;
             a_lo += slab16;
             if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
           }
+          DMD_TS(1, it, 14);
         }
       } else {
       uint32_t stage = 0, phase = 0, a_lo = a_lo0;
@@ -740,7 +754,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
       float* bnd = reinterpret_cast<float*>(smem + L.stage_off);
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
-        epi.tile(p, sbias, bnd, tmem_base + (uint32_t)b * kAccCols, tile_begin + it, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b);
+        epi.tile(p, sbias, bnd, tmem_base + (uint32_t)b * kAccCols, tile_begin + it, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b, it);
       }
       epi.finish(p);
     } else if constexpr (kGroups == 0) {

@@ -13,7 +13,7 @@ from torch.distributions.categorical import Categorical
 
 from .. import _lib
 from ..coroutines.env_loop import make_env_loop
-from ..utils import LossAndLogs, init_lstm
+from ..utils import LossAndLogs, NativeStateMixin, init_lstm
 from .blocks import SmallResBlock, _NativeOnly, conv3x3
 
 ActorCriticOutput = namedtuple("ActorCriticOutput", "logits_act val hx_cx")
@@ -50,7 +50,7 @@ class ActorCriticEncoder(_NativeOnly):  # actor_critic.py:101-113 (parameter con
         self.encoder = nn.Sequential(*layers)
 
 
-class ActorCritic(nn.Module):
+class ActorCritic(NativeStateMixin, nn.Module):
     def __init__(self, cfg: ActorCriticConfig) -> None:
         super().__init__()
         self.cfg = cfg
@@ -105,7 +105,7 @@ class ActorCritic(nn.Module):
             if not h:
                 raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
             self._h = h
-        tensors = list(self.state_dict(keep_vars=True).values())
+        tensors = self._state_tensors()
         wkey = tuple((t.data_ptr(), t._version) for t in tensors)
         if wkey != self._wkey:
             n = lib.dmd_actor_critic_num_tensors(self._h)
@@ -117,9 +117,6 @@ class ActorCritic(nn.Module):
             _lib.check(lib.dmd_actor_critic_set_weights(self._h, arr, n, self._packed.data_ptr(), _lib.current_stream()))
             self._wkey = wkey
         return self._h
-
-    def _state_tensors(self):
-        return list(self.state_dict(keep_vars=True).values())
 
     def grad_layout(self):
         lib = _lib.lib()

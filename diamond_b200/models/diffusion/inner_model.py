@@ -8,6 +8,7 @@ from torch import Tensor
 import torch.nn as nn
 
 from ... import _lib
+from ...utils import NativeStateMixin
 from ..blocks import FourierFeatures, GroupNorm, UNet, conv3x3
 
 
@@ -22,7 +23,7 @@ class InnerModelConfig:  # inner_model.py:13-21
     num_actions: Optional[int] = None
 
 
-class InnerModel(nn.Module):
+class InnerModel(NativeStateMixin, nn.Module):
     def __init__(self, cfg: InnerModelConfig) -> None:  # inner_model.py:24-42 (same registration order)
         super().__init__()
         self.cfg = cfg
@@ -78,7 +79,7 @@ class InnerModel(nn.Module):
             if not h:
                 raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
             self._h, self._h_key, self._wkey, self._packed = h, key, None, None
-        tensors = list(self.state_dict(keep_vars=True).values())
+        tensors = self._state_tensors()
         wkey = tuple((t.data_ptr(), t._version) for t in tensors)
         if wkey != self._wkey:
             n = lib.dmd_denoiser_num_tensors(self._h)

@@ -14,7 +14,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from .. import _lib
-from ..utils import init_lstm
+from ..utils import NativeStateMixin, init_lstm
 from .blocks import Downsample, ResBlocks, _NativeOnly, conv3x3
 
 
@@ -44,7 +44,7 @@ class RewEndEncoder(_NativeOnly):  # rew_end_model.py:93-125 (parameter containe
         self.downsamples = nn.ModuleList([nn.Identity()] + [Downsample(c) for c in channels[:-1]] + [nn.Identity()])
 
 
-class RewEndModel(nn.Module):
+class RewEndModel(NativeStateMixin, nn.Module):
     def __init__(self, cfg: RewEndModelConfig) -> None:  # rew_end_model.py:27-41 (same registration order)
         super().__init__()
         self.cfg = cfg
@@ -89,7 +89,7 @@ class RewEndModel(nn.Module):
             if not h:
                 raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
             self._h, self._h_dev, self._wkey, self._packed, self._ws = h, dev.index, None, None, None
-        tensors = list(self.state_dict(keep_vars=True).values())
+        tensors = self._state_tensors()
         wkey = tuple((t.data_ptr(), t._version) for t in tensors)
         if wkey != self._wkey:
             n = lib.dmd_rew_end_num_tensors(self._h)

@@ -21,6 +21,29 @@ def init_lstm(model: nn.Module) -> None:
             p.data.fill_(0)
 
 
+class NativeStateMixin:
+    """Modules with a native executor check on every call whether a parameter changed (data_ptr, _version) before reusing the
+    packed fp16 copies.  Walking state_dict() for that costs ~0.4 ms per call on the 235 tensors of the denoiser; the tensor
+    list is therefore cached and dropped whenever `_apply` (to / cuda / float ...) may have replaced tensors.  In-place updates
+    (optimizer steps, load_state_dict, p.data.copy_) keep the objects and bump `_version`, which the key sees; code that REPLACES
+    a Parameter object or writes through `.data.fill_` must call `refresh_weights()`."""
+
+    def _state_tensors(self):
+        ts = self.__dict__.get("_state_tensor_cache")
+        if ts is None:
+            ts = list(self.state_dict(keep_vars=True).values())
+            self.__dict__["_state_tensor_cache"] = ts
+        return ts
+
+    def refresh_weights(self) -> None:
+        self.__dict__["_state_tensor_cache"] = None
+        self.__dict__["_wkey"] = None
+
+    def _apply(self, fn, recurse=True):
+        self.__dict__["_state_tensor_cache"] = None
+        return super()._apply(fn, recurse)
+
+
 # ----------------------------------------------------------------------------------------------- data-parallel plumbing
 # SURVEY.md 8 a26.  The reference wraps each agent module in torch DDP (utils.py:105-106, trainer.py:110) and relies on
 # autograd hooks to average gradients.  A native executor produces all gradients of a module in one C-ABI call, outside

@@ -75,6 +75,21 @@ def main():
         loss, _ = ac()
         loss.backward()
     print("ActorCritic.forward() + backward, 15 steps ms:", round(timed(update, reps=3, warm=1), 3))
+
+    def fwd_only():
+        with torch.no_grad():
+            pass
+        loss, _ = ac()
+        return loss
+    print("ActorCritic.forward() alone, 15 steps       ms:", round(timed(fwd_only, reps=3, warm=1), 3))
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    update()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
     # python-side cost of the native plumbing
     t0 = time.perf_counter()
     for _ in range(100):
