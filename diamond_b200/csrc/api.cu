@@ -197,6 +197,8 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   DMD_CHECK(stages >= 2, "conv: shared memory too small for W=%d Cin=%d CoutPad=%d", p->W, p->Cin, p->CoutPad);
   p->stages = stages;
   p->egroups = groups;
+  // row-stacked mode: two epilogue groups on alternate tiles once a CTA sees more than one tile
+  p->trs_groups = (p->trs && tune_int("DMD_TRS_GROUPS", 2) == 2 && p->num_tiles > 148) ? 2 : 1;
   *smem = conv_smem_layout(w_bytes, p->CoutPad, p->Palloc, stages, groups).total;
   *tmem_cols = d->CoutPad <= 32 ? 32 : (d->CoutPad <= 64 ? 64 : 128);
   if (p->trs) *tmem_cols = 3 * d->CoutPad <= 64 ? 64 : (3 * d->CoutPad <= 128 ? 128 : 256);   // accumulator = three column blocks

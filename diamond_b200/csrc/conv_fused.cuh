@@ -13,7 +13,7 @@
 // The fused 1x1 skip projection (blocks.py:133,142,145) takes its split-fp16 operand [x_hi | x_lo | x_hi] from the RAW block
 // input the same way (centre tap only, no halo).
 //
-// Roles (320 threads): warp 1 allocates TMEM, then issues every tcgen05.mma once the operand is complete; all other warps
+// Roles (352 threads): warp 1 allocates TMEM, then issues every tcgen05.mma once the operand is complete; all other warps
 // transform; warps 2-9 then run the direct epilogue.  Weights arrive by bulk copy during the transform.
 #pragma once
 #include "conv_tc.cuh"
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_fused_kernel(const Fused
 
   if (warp != 1) {
     // =========================================================================================== TRANSFORM (288 threads)
-    const int tt = warp == 0 ? lane : tid - 32;        // 0..287
+    const int tt = warp == 0 ? lane : tid - 32;        // 0 .. kConvThreads - 33
     constexpr int NT = kConvThreads - 32;
     // ---- main operand: items = (position p in the halo window, 16-channel group g); consecutive threads take the groups of one
     //      pixel (contiguous 64-byte pieces of one NHWC row)
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_fused_kernel(const Fused
     }
     if (elect_one_sync()) umma_commit(tfull);
     __syncwarp();
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < kProdWarp2) {
     // =========================================================================================== EPILOGUE
     DirectEpilogue<kAccCols> epi;
     epi.init(p, warp, lane);

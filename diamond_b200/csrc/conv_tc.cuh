@@ -34,7 +34,8 @@ namespace dmd {
 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = (2 + kEpiWarps) * 32;  // 320
+constexpr int kConvThreads = (3 + kEpiWarps) * 32;  // 352: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue, warp 10 second producer
+constexpr int kProdWarp2 = 2 + kEpiWarps;
 constexpr int kTileM = 128;
 constexpr int kMaxCin = 128;        // channels of one activation source
 constexpr int kMaxKChannels = 384;  // K extent per tap: up to 3 x 128 (split-fp16 "precise" convs)
@@ -92,6 +93,7 @@ struct ConvParams {
   int num_tiles, stages;
   int trs;              // tap-row-stacked mode (see TrsEpilogue): weights [dy][Cin/8][3*CoutPad][8], tiles advance by 126 positions
   int tile_stride;      // 128, or 126 in trs mode
+  int trs_groups;       // trs mode: 1 = eight warps per tile, 2 = two groups of four warps on alternate tiles
   int egroups;          // epilogue groups: 1 = eight warps share every tile; 2 = two groups of four warps take alternate tiles
   FastDiv dPW, dPH;
   int dbg;
@@ -115,10 +117,10 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(uint32_t w_bytes, int
   L.sstat_off = L.rowinfo_off + (uint32_t)groups * kTileM * 8;   // [epilogue warp 8][slot 3][group 4][2] floats
   L.stage_pitch = (uint32_t)CoutPad * 4 + 16;
   L.stage_off = (L.sstat_off + (groups ? kEpiWarps * kStatSlots * kMaxOutGroups * 2 * 4 : 0) + 127u) & ~127u;
-  if (groups == 3) {   // tap-row-stacked: no staging, a boundary-row exchange buffer [parity 2][kind 2][quarter 4][128] floats instead
+  if (groups == 3) {   // tap-row-stacked: no staging, a boundary-row exchange buffer (16 KB) instead
     L.rowinfo_off = L.sstat_off = L.bias_off + 128 * 4;
     L.stage_off = L.rowinfo_off;
-    L.w_off = (L.stage_off + 2u * 2u * 4u * 128u * 4u + 127u) & ~127u;
+    L.w_off = (L.stage_off + 2u * 2u * 2u * 4u * 128u * 4u + 127u) & ~127u;   // [group 2][parity 2][kind 2][quarter 4][128] floats
     L.a_off = (L.w_off + w_bytes + 127u) & ~127u;
     L.slab_bytes = 2u * Palloc * 16;
     L.total = L.a_off + (uint32_t)stages * L.slab_bytes + 16;
@@ -323,23 +325,34 @@ struct DirectEpilogue {
 template <int kAccCols>
 struct TrsEpilogue {
   int quarter, blk_begin, blk_end, g, lc, G, my_grp, lane;
+  int grp, bar_id, bar_threads;       // epilogue group (two groups of four warps take alternate tiles), its named barrier
   bool vec2;
-  float s0, s1, s2, ss0, ss1, ss2;
+  float s0, s1, s2, ss0, ss1, ss2;   // partial sums of the warp's first GroupNorm group ...
+  float t0, t1, t2, tt0, tt1, tt2;   // ... and of its second one (a warp that owns all 64 columns spans two groups)
   int n_cur;
 
-  __device__ __forceinline__ void init(const ConvParams& p, int warp, int lane_) {
+  // ngroups == 1: the eight warps share every tile (two warps per TMEM lane quarter split the columns).
+  // ngroups == 2: two groups of four warps take alternate tiles / accumulators, each warp owns all columns of its quarter: the
+  //               stores of one tile (32 KB at ~16 B/clk/SM: ~2 k cycles, the longest phase) drain while the other group loads
+  //               and combines the next tile.
+  __device__ __forceinline__ void init(const ConvParams& p, int warp, int lane_, int ngroups) {
     lane = lane_;
     const int ew = warp - 2;
     quarter = warp & 3;
-    const int half = ew >> 2;
     const int nblk = p.CoutPad >> 3;
-    const int hb = nblk >> 1;                  // CoutPad is a multiple of 16: equal halves (every warp runs the same number of chunks)
-    blk_begin = half ? hb : 0; blk_end = half ? nblk : hb;
+    if (ngroups == 2) {
+      grp = ew >> 2; blk_begin = 0; blk_end = nblk; bar_id = 1 + grp; bar_threads = kEpiThreads / 2;
+    } else {
+      const int half = ew >> 2;
+      const int hb = nblk >> 1;                // CoutPad is a multiple of 16: equal halves (every warp runs the same number of chunks)
+      grp = 0; blk_begin = half ? hb : 0; blk_end = half ? nblk : hb; bar_id = 1; bar_threads = kEpiThreads;
+    }
     g = lane >> 2; lc = (lane & 3) * 2;
     vec2 = (p.Cout & 1) == 0;
     G = p.ostats ? p.Cout / p.ogs : 1;
     my_grp = p.ostats ? min(G - 1, (blk_begin * 8) / p.ogs) : 0;
     s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+    t0 = t1 = t2 = tt0 = tt1 = tt2 = 0.f;
     n_cur = -1;
   }
 
@@ -364,12 +377,34 @@ struct TrsEpilogue {
       }
     }
     s0 = s1 = s2 = ss0 = ss1 = ss2 = 0.f;
+    if (my_grp + 1 < G && (blk_end - blk_begin) * 8 > p.ogs) {   // the warp's columns reach into a second group
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, m);
+        tt0 += __shfl_xor_sync(0xffffffffu, tt0, m);
+        if (multi) {
+          t1 += __shfl_xor_sync(0xffffffffu, t1, m);
+          tt1 += __shfl_xor_sync(0xffffffffu, tt1, m);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, m);
+          tt2 += __shfl_xor_sync(0xffffffffu, tt2, m);
+        }
+      }
+      if (lane == 0) {
+        double* dst = p.ostats + ((size_t)img0 * G + my_grp + 1) * 2;
+        if (img0 < p.B && (t0 != 0.f || tt0 != 0.f)) { atomicAdd(dst, (double)t0); atomicAdd(dst + 1, (double)tt0); }
+        if (multi) {
+          if (img0 + 1 < p.B && (t1 != 0.f || tt1 != 0.f)) { atomicAdd(dst + (size_t)G * 2, (double)t1); atomicAdd(dst + (size_t)G * 2 + 1, (double)tt1); }
+          if (img0 + 2 < p.B && (t2 != 0.f || tt2 != 0.f)) { atomicAdd(dst + (size_t)G * 4, (double)t2); atomicAdd(dst + (size_t)G * 4 + 1, (double)tt2); }
+        }
+      }
+      t0 = t1 = t2 = tt0 = tt1 = tt2 = 0.f;
+    }
   }
 
   // tile index ti: window rows r = 0..127 are positions w0 + r, w0 = 126 * ti - 1; outputs are rows 1..126.
   // bnd: shared exchange buffer [parity 2][kind 2 (0: row 31 of D_-1, 1: row 0 of D_+1)][quarter 4][128] floats
   __device__ __forceinline__ void tile(const ConvParams& p, const float* sbias, float* bnd, uint32_t tmem_acc, int ti, uint64_t* tfull,
-                                       uint32_t parity, uint64_t* tempty, int it = 0) {
+                                       uint32_t parity, uint64_t* tempty, int it = 0, int xpar = 0) {
     (void)it;
     const bool ts = threadIdx.x == 64;   // timeline stamps (DMD_TIMELINE builds): first epilogue thread
     (void)ts;
@@ -400,8 +435,8 @@ struct TrsEpilogue {
         if (valid) { opix[j] = (n * Ho + yo) * Wo + xo; slot[j] = n - n_lo; }
       }
     }
-    float* bup = bnd + (size_t)((ti & 1) * 2 + 0) * 4 * 128;    // [quarter][col]: row 31 of the D_-1 block
-    float* bdn = bnd + (size_t)((ti & 1) * 2 + 1) * 4 * 128;    //                 row 0 of the D_+1 block
+    float* bup = bnd + (size_t)(((grp * 2 + xpar) * 2 + 0) * 4) * 128;    // [quarter][col]: row 31 of the D_-1 block
+    float* bdn = bnd + (size_t)(((grp * 2 + xpar) * 2 + 1) * 4) * 128;    //                 row 0 of the D_+1 block
     bool waited = false;
     auto chunk = [&](auto nbc, auto vecc, int blk) {
       constexpr int NB = decltype(nbc)::value;
@@ -453,7 +488,7 @@ struct TrsEpilogue {
         }
       }
       if (ts && blk == blk_begin) DMD_TS(2, it, 2);
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(bar_id, bar_threads);
       if (ts && blk == blk_begin) DMD_TS(2, it, 8);
       const int src_up = (lane - 4) & 31, src_dn = (lane + 4) & 31;
       float2 bv[NB];
@@ -502,9 +537,15 @@ struct TrsEpilogue {
           }
           if (p.ostats != nullptr) {
             const int sl = single_image ? 0 : slot[j];
-            s0 += (sl == 0) ? sps : 0.f;  ss0 += (sl == 0) ? spss : 0.f;
-            s1 += (sl == 1) ? sps : 0.f;  ss1 += (sl == 1) ? spss : 0.f;
-            s2 += (sl == 2) ? sps : 0.f;  ss2 += (sl == 2) ? spss : 0.f;
+            if ((blk - blk_begin) * 8 < p.ogs) {     // chunk inside the warp's first group (uniform per chunk)
+              s0 += (sl == 0) ? sps : 0.f;  ss0 += (sl == 0) ? spss : 0.f;
+              s1 += (sl == 1) ? sps : 0.f;  ss1 += (sl == 1) ? spss : 0.f;
+              s2 += (sl == 2) ? sps : 0.f;  ss2 += (sl == 2) ? spss : 0.f;
+            } else {
+              t0 += (sl == 0) ? sps : 0.f;  tt0 += (sl == 0) ? spss : 0.f;
+              t1 += (sl == 1) ? sps : 0.f;  tt1 += (sl == 1) ? spss : 0.f;
+              t2 += (sl == 2) ? sps : 0.f;  tt2 += (sl == 2) ? spss : 0.f;
+            }
           }
         }
       }
@@ -570,7 +611,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, (kGroups == 0 || kGroups == 3) ? kEpiWarps : kEpiWarps / kGroups); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kGroups == 3 ? kEpiWarps / p.trs_groups : (kGroups == 0 ? kEpiWarps : kEpiWarps / kGroups)); }
     fence_mbar_init();
     const uint32_t tap_bytes = (uint32_t)p.Cin * p.CoutPad * 2;
     const uint32_t extra_bytes = (uint32_t)p.Cextra * p.CoutPad * 2;
@@ -591,28 +632,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   pdl_wait();  // operands / residual / statistics come from earlier kernels
   if (blockIdx.x == 0 && tid == 64) ktrace_stamp(p.ktrace);
 
-  if (warp == 0) {
-    // =========================================================================================== PRODUCER (TMA)
+  if (warp == 0 || warp == kProdWarp2) {
+    // =========================================================================================== PRODUCERS (TMA)
+    // Two producer warps take alternate slabs of the global slab sequence.  One warp spends ~200 cycles per slab (the wait on
+    // the `empty` barrier alone is ~130 even when the phase has completed), which is slower than the tensor pipe consumes the
+    // centre-tap slabs of a fused projection (one MMA each): with 28 slabs per tile and a 12-stage ring the single producer
+    // set the tile time of those convs (11.6 k cycles per tile measured vs ~2.9 k of MMA work).
     {  // converged warp, one elected lane issues the copies (uniform-register operands)
+      const uint32_t pid = (warp == 0) ? 0u : 1u;
       const uint32_t chunk_bytes = (uint32_t)p.P * 16;
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, nslab = 0;
       for (int it = 0; it < my_tiles; ++it) {
         // first halo position of this tile inside a plane (guard G keeps it non-negative)
         const size_t pos0 = (size_t)((tile_begin + it) * p.tile_stride - lead - halo + p.G) * 16;
         int seg = 0, seg_ks = 0;  // current operand segment and slab index inside it
-        for (int ks = 0; ks < kslabs; ++ks) {
-          DMD_TS(0, it, (ks & 3) * 3 + 0);
-          mbar_wait(empty + stage, phase ^ 1u);
-          DMD_TS(0, it, (ks & 3) * 3 + 1);
-          if (elect_one_sync()) {
-            uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
-            mbar_expect_tx(full + stage, 2 * chunk_bytes);
-            const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
-            bulk_g2s(slab, plane, chunk_bytes, full + stage);
-            bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+        for (int ks = 0; ks < kslabs; ++ks, ++nslab) {
+          if ((nslab & 1u) == pid) {
+            DMD_TS(0, it, (ks & 3) * 3 + 0);
+            mbar_wait(empty + stage, phase ^ 1u);
+            DMD_TS(0, it, (ks & 3) * 3 + 1);
+            if (elect_one_sync()) {
+              uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
+              mbar_expect_tx(full + stage, 2 * chunk_bytes);
+              const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
+              bulk_g2s(slab, plane, chunk_bytes, full + stage);
+              bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+            }
+            __syncwarp();
+            DMD_TS(0, it, (ks & 3) * 3 + 2);
           }
-          __syncwarp();
-          DMD_TS(0, it, (ks & 3) * 3 + 2);
           if (++seg_ks == p.seg_slabs[seg]) { seg_ks = 0; ++seg; }
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
@@ -750,11 +798,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
     if constexpr (kGroups == 3) {
       // ---- tap-row-stacked epilogue: three row-shifted accumulator blocks -> registers -> global (TrsEpilogue above)
       TrsEpilogue<kAccCols> epi;
-      epi.init(p, warp, lane);
+      epi.init(p, warp, lane, p.trs_groups);
       float* bnd = reinterpret_cast<float*>(smem + L.stage_off);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int b = it & 1;
-        epi.tile(p, sbias, bnd, tmem_base + (uint32_t)b * kAccCols, tile_begin + it, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b, it);
+      for (int it = epi.grp; it < my_tiles; it += p.trs_groups) {
+        const int b = it & 1;                    // two groups: accumulator b belongs to group b
+        const int xpar = p.trs_groups == 2 ? ((it >> 1) & 1) : (it & 1);
+        epi.tile(p, sbias, bnd, tmem_base + (uint32_t)b * kAccCols, tile_begin + it, tfull + b, ((uint32_t)it >> 1) & 1u, tempty + b, it, xpar);
       }
       epi.finish(p);
     } else if constexpr (kGroups == 0) {
