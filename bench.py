@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "imagined frames/sec (64x64, 3 denoise steps)"
 GFLOP_PER_FRAME = 18.266  # 3 x 6.0888 GFLOP denoiser forwards
-TRS = os.environ.get("DMD_CONV_TRS", "1") != "0"  # the executor's weight layout for 3x3 convs (tap-row-stacked unless switched off)
+TRS = os.environ.get("DMD_CONV_TRS", "0") != "0"  # the executor's weight layout for 3x3 convs (tap-major; DMD_CONV_TRS=1 selects the tap-row-stacked experiment)
 
 
 def load_peaks():
@@ -424,13 +424,22 @@ def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1
     randomize_module_(ac, 2026)
     den, rem, ac = den.to(dev).eval(), rem.to(dev).eval(), ac.to(dev).train()
 
+    # A trained reward/termination model ends episodes rarely; a random-init one ends ~half of them at every step, which turns the
+    # rollout into a stream of resets + burn-ins.  The synthetic model's two termination logits are therefore tied to
+    # +/- 0.05 * sum(hidden) (the head has no bias, rew_end_model.py:40), i.e. P(end) of a few per cent.
+    with torch.no_grad():
+        last = [m for m in rem.modules() if isinstance(m, torch.nn.Linear)][-1]
+        last.weight[3].fill_(0.05); last.weight[4].fill_(-0.05)
+
+    pool = [frame_stacks(envs, 4, 3, 64, 64, 4, 1000 * (rank + 1) + k)[:2] for k in range(8)]   # in-memory "dataset": no per-batch RNG cost
+
     class Loader:
         batch_sampler = types.SimpleNamespace(batch_size=envs)
 
         def __iter__(self):
             k = 0
             while True:
-                obs, act, _ = frame_stacks(envs, 4, 3, 64, 64, 4, 1000 * (rank + 1) + k)  # seq_length = num_steps_conditioning (trainer.py:149)
+                obs, act = pool[k % len(pool)]
                 k += 1
                 yield types.SimpleNamespace(obs=obs, act=act)
 

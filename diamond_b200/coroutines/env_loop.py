@@ -46,7 +46,7 @@ class ImaginationLoop:
         infos: List[Dict[str, Any]] = []
         for t in range(num_steps):
             logits, val, (hx, cx) = model.predict_act_value(obs, (hx, cx))
-            act = Categorical(logits=logits).sample()
+            act = Categorical(logits=logits, validate_args=False).sample()   # validate_args costs a device->host sync per call
             if random.random() < self.epsilon:                    # drawn every step, like the reference (env_loop.py:34)
                 act = torch.randint(low=0, high=env.num_actions, size=(b,), device=dev)
             nxt, rew, end, trunc, info = env.step(act)

@@ -141,12 +141,15 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
       const uint8_t* xh[2] = {(const uint8_t*)d->xsrc0, (const uint8_t*)d->xsrc1};
       const uint8_t* xl[2] = {(const uint8_t*)d->xsrc0_lo, (const uint8_t*)d->xsrc1_lo};
       const int xc[2] = {d->xC0, d->xC1};
-      for (int rep = 0; rep < 3; ++rep)
+      // the hi parts are loaded ONCE and multiplied by both W_hi and W_lo (two MMAs per slab), the lo parts by W_hi: 2/3 of the
+      // slabs of the naive [x_hi | x_lo | x_hi] K order, and each slab holds only the tile's own 128 rows (centre tap: no halo)
+      for (int rep = 0; rep < 2; ++rep)
         for (int k = 0; k < (d->xC1 ? 2 : 1); ++k) {
           DMD_CHECK(n < kMaxSegs, "conv: too many operand segments");
           p->seg_base[n] = (rep == 1) ? xl[k] : xh[k]; p->seg_slabs[n] = xc[k] / 16; ++n;
         }
       p->Cextra = 3 * (d->xC0 + d->xC1);
+      p->xslabs = 2 * (d->xC0 + d->xC1) / 16;
       p->wpk_extra = reinterpret_cast<const __half*>(d->wpk_x);
       p->bias_extra = d->bias_x;
     }
@@ -178,7 +181,7 @@ static int conv_fill(const dmd_conv_desc* d, ConvParams* p, size_t* smem, int* t
   p->num_tiles = (g.Q + p->tile_stride - 1) / p->tile_stride;
   // slab ring: everything that fits next to the resident weights, at most four tiles' worth.  Two epilogue groups (each with
   // its own staging tile) when the ring still gets >= 4 slabs and a CTA sees at least two tiles; else one group.
-  const int kslabs = (p->Cin + p->Cextra) / 16;
+  const int kslabs = p->Cin / 16 + p->xslabs;
   const uint32_t w_bytes = conv_weight_bytes(p->taps, p->Cin, p->Cextra, p->CoutPad);
   // epilogue organisation: direct (0) unless switched off (DMD_CONV_EPI=0) or a warp's columns would span several GroupNorm groups
   const bool direct = tune_int("DMD_CONV_EPI", 1) != 0 && (!d->out_stats || d->CoutPad <= 64);
@@ -363,7 +366,7 @@ extern "C" int dmd_conv_plan(const dmd_conv_desc* d, dmd_conv_plan_info* out) {
   DMD_CHECK(d && out, "conv_plan: null argument");
   ConvParams p; size_t smem; int cols;
   if (conv_fill(d, &p, &smem, &cols)) return 1;
-  out->tiles = p.num_tiles; out->kslabs = (p.Cin + p.Cextra) / 16; out->stages = p.stages; out->tmem_cols = cols;
+  out->tiles = p.num_tiles; out->kslabs = p.Cin / 16 + p.xslabs; out->stages = p.stages; out->tmem_cols = cols;
   out->smem_bytes = smem; out->weight_bytes = conv_weight_bytes(p.taps, p.Cin, p.Cextra, p.CoutPad);
   return 0;
 }
@@ -731,7 +734,9 @@ struct Walker {  // assigns state_dict indices in module registration order and 
     ConvW c; c.w_idx = next((long long)cout * cin_real * taps); c.b_idx = next(cout);
     c.Cout = cout; c.CoutPad = round_up(cout, 16); c.CinReal = cin_real; c.taps = taps;
     c.c0_real = c0_real; c.c0_store = c0_store; c.Cin = round_up(c0_store + c1, 16); c.precise = precise;
-    c.trs = (taps == 9 && !precise && 3 * c.CoutPad <= 256 && tune_int("DMD_CONV_TRS", 1) != 0) ? 1 : 0;
+    // tap-row-stacked layout: opt-in (DMD_CONV_TRS=1).  Correct (tests/test_gpu_conv.py runs it), but measured slower on the B200:
+    // 25 us vs 20 us for the 64->64 conv at 64x64 -- see DESIGN.md section 4
+    c.trs = (taps == 9 && !precise && 3 * c.CoutPad <= 256 && tune_int("DMD_CONV_TRS", 0) != 0) ? 1 : 0;
     c.pk_off = pk; pk += (size_t)taps * c.Cin * c.CoutPad * 2 * (precise ? 3 : 1); pk = (pk + 255) & ~(size_t)255;
     if (dgrad) {
       c.nsrcT = c1 ? 2 : 1;

@@ -76,6 +76,7 @@ struct ConvParams {
                         // projection r = proj(cat(x, skip)) accumulated into the same TMEM tile (blocks.py:133,142,145)
   const __half* wpk_extra;  // [1][Cextra/8][CoutPad][8]
   const float* bias_extra;  // [Cout] or null
+  int xslabs;               // operand slabs of the projection that are LOADED: hi and lo parts once each (2 * channels / 16)
   int B, H, W;          // conv input size
   int taps;             // 9 (3x3, pad 1) or 1 (1x1)
   int stride;           // 1 or 2 (stride 2 == stride-1 result sampled at even (y,x); exact for k=3,p=1)
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
   const int lead = p.trs ? 1 : 0;            // window rows in front of the first output row
   const int S = p.stages;
   const int main_slabs = p.Cin >> 4;
-  const int kslabs = main_slabs + (p.Cextra >> 4);
+  const int kslabs = main_slabs + p.xslabs;   // slabs that travel through the ring (the projection's hi slabs feed two MMAs)
   const uint32_t w_main_bytes = ((uint32_t)p.taps * p.Cin * p.CoutPad * 2 + 127u) & ~127u;
   // contiguous, balanced tile range per CTA: neighbouring tiles share halo rows (L2 hits)
   const int tiles_lo = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
@@ -653,10 +654,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             DMD_TS(0, it, (ks & 3) * 3 + 1);
             if (elect_one_sync()) {
               uint8_t* slab = sA + (size_t)stage * L.slab_bytes;
-              mbar_expect_tx(full + stage, 2 * chunk_bytes);
-              const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0;
-              bulk_g2s(slab, plane, chunk_bytes, full + stage);
-              bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, chunk_bytes, full + stage);
+              // projection slabs (centre tap only): the tile's own 128 rows, no halo
+              const bool xs = ks >= main_slabs;
+              const uint32_t bytes = xs ? (uint32_t)kTileM * 16 : chunk_bytes;
+              mbar_expect_tx(full + stage, 2 * bytes);
+              const uint8_t* plane = p.seg_base[seg] + (size_t)(2 * seg_ks) * p.plane_bytes + pos0 + (xs ? (size_t)halo * 16 : 0);
+              bulk_g2s(slab, plane, bytes, full + stage);
+              bulk_g2s(slab + (size_t)p.Palloc * 16, plane + p.plane_bytes, bytes, full + stage);
             }
             __syncwarp();
             DMD_TS(0, it, (ks & 3) * 3 + 2);
@@ -719,10 +723,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
             tc_fence_after_sync();
             if (elect_one_sync()) {
               if (ks >= main_slabs) {
-                // fused 1x1 projection: centre tap, N = CoutPad, accumulated into the dx = 0 column block
-                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + pw);
-                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
+                // fused 1x1 projection: centre tap, N = CoutPad, accumulated into the dx = 0 column block (hi slabs: two MMAs)
+                const uint32_t e = (uint32_t)(ks - main_slabs), ng = (uint32_t)p.xslabs >> 1;
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)a_lo;
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + e * kstep16);
                 umma_f16(d_tmem + (uint32_t)p.CoutPad, ad, bd, idesc, 1u);
+                if (e < ng) {
+                  const uint64_t bd2 = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (2u * ng + e) * kstep16);
+                  umma_f16(d_tmem + (uint32_t)p.CoutPad, ad, bd2, idesc, 1u);
+                }
               } else {
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
@@ -762,10 +771,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvPara
           if (elect_one_sync()) {
             if (!DMD_DBG(2)) {
               if (ks >= main_slabs) {
-                // fused projection: centre tap only, its own weight block
-                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)halo);
-                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (uint32_t)(ks - main_slabs) * kstep16);
+                // fused projection (centre tap, slab = the tile's rows): weights [W_hi | W_hi | W_lo] along K; a hi slab of group g
+                // meets W_hi (block g) and W_lo (block 2*ng + g), a lo slab W_hi (block ng + g)
+                const uint32_t e = (uint32_t)(ks - main_slabs), ng = (uint32_t)p.xslabs >> 1;
+                const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)a_lo;
+                const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + e * kstep16);
                 umma_f16(d_tmem, ad, bd, idesc, 1u);
+                if (e < ng) {
+                  const uint64_t bd2 = ((uint64_t)hi << 32) | (uint64_t)(b_x0 + (2u * ng + e) * kstep16);
+                  umma_f16(d_tmem, ad, bd2, idesc, 1u);
+                }
               } else if (nine) {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {

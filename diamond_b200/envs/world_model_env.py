@@ -174,6 +174,6 @@ class WorldModelEnv:
         last = self._slot(t - 1)
         logits_rew, logits_end, (self.hx_rew_end, self.cx_rew_end) = self.rew_end_model.predict_rew_end(
             self._frames[last].unsqueeze(1), self._acts[last].unsqueeze(1), next_obs, (self.hx_rew_end, self.cx_rew_end))
-        rew = Categorical(logits=logits_rew).sample().squeeze(1) - 1.0  # {-1, 0, 1}
-        end = Categorical(logits=logits_end).sample().squeeze(1)
+        rew = Categorical(logits=logits_rew, validate_args=False).sample().squeeze(1) - 1.0  # {-1, 0, 1}
+        end = Categorical(logits=logits_end, validate_args=False).sample().squeeze(1)
         return rew, end

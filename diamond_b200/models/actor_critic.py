@@ -174,7 +174,7 @@ class ActorCritic(NativeStateMixin, nn.Module):
         """REINFORCE with a lambda-return baseline over one imagined rollout of `backup_every` steps."""
         cfg = self.loss_cfg
         _, act, rew, end, trunc, logits, val, val_bootstrap, _ = self.env_loop.send(cfg.backup_every)
-        policy = Categorical(logits=logits)
+        policy = Categorical(logits=logits, validate_args=False)
         entropy = policy.entropy().mean()
         target = compute_lambda_returns(rew, end, trunc, val_bootstrap, cfg.gamma, cfg.lambda_)
         advantage = (target - val).detach()

@@ -47,7 +47,7 @@ def test_dominant_conv_plan():
     (dict(C0=64, C1=64, src1=P), 8, 64),                                              # u-block conv1: x || skip
     (dict(C0=16, precise=1, src0_lo=P), 3, 64),                                       # conv_in, split-fp16
     (dict(C0=64, Cout=3, CoutPad=16), 4, 32),                                         # conv_out
-    (dict(C0=64, xsrc0=P, xsrc0_lo=P, xsrc1=P, xsrc1_lo=P, xC0=64, xC1=64, wpk_x=P), 4 + 24, 64),  # conv2 + fused projection
+    (dict(C0=64, xsrc0=P, xsrc0_lo=P, xsrc1=P, xsrc1_lo=P, xC0=64, xC1=64, wpk_x=P), 4 + 16, 64),  # conv2 + fused projection: hi and lo slabs once each (24 MMAs)
     (dict(C0=64, taps=1), 4, 64),
     (dict(C0=64, CoutPad=128, Cout=128, H=32, W=32), 4, 128),                         # 147 KB of weights: narrow images only
 ])
