@@ -590,6 +590,17 @@ extern "C" int dmd_nhwc_to_nchw(const float* in, float* out, int B, int C, int C
 }
 
 // ---------------------------------------------------------------------------------------------- denoiser executor
+// zero-pad / crop copy of an NHWC tensor, then the GroupNorm partial sums of the result (the consumer's prologue reads them)
+static int resize_launch(const ResizeParams& p, cudaStream_t st) {
+  const long long total = (long long)p.B * p.Hd * p.Wd * (p.C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  resize_nhwc_kernel<<<(int)blocks, 256, 0, st>>>(p);
+  DMD_LAUNCH_OK();
+  if (p.stats) return dmd_gn_stats(p.dst, p.stats, p.B, p.Hd * p.Wd, p.C, p.gs, st);
+  return 0;
+}
+
 namespace {
 
 constexpr float kGnEps = 1e-5f;  // blocks.py:13
@@ -615,8 +626,8 @@ struct ResBlockW {
 
 struct Tens { float* data; double* stats; int C, H, W, gs; float* grad = nullptr; int gid = -1; };
 
-enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2, OP_FUSED = 3 };
-struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; FusedParams fused; };
+enum OpKind { OP_CONV = 0, OP_ATTN = 1, OP_PREP = 2, OP_FUSED = 3, OP_RESIZE = 4 };
+struct Op { int kind; ConvParams conv; size_t smem; int cols; AttnParams attn; PrepParams prep; int prep_nsrc; FusedParams fused; ResizeParams rs; };
 constexpr int kScratchSlots = 10;  // round-robin pool of PLC16 operand buffers (each lives from its prep to the next conv)
 
 // PLC16 operands produced by one prep launch (op = index of that launch in Plan::ops, replayed by the backward pass)
@@ -1016,15 +1027,26 @@ struct PlanBuilder {
     return err;
   }
 
+  void resize(const Tens& src, const Tens& dst) {
+    Op op; op.kind = OP_RESIZE;
+    op.rs = ResizeParams{src.data ? src.data : (const float*)1, dst.data ? dst.data : (float*)1, pl->B, src.H, src.W, dst.H, dst.W, src.C,
+                         dst.stats ? dst.stats : (double*)1, dst.gs};
+    pl->ops.push_back(op);
+  }
+
   int build() {
     const dmd_denoiser_config& c = h->cfg;
     const int L = c.num_levels, B = pl->B, H = pl->H, W = pl->W;
     const int div = 1 << (L - 1);
-    if (H % div || W % div) return fail("denoiser: H=%d W=%d must be multiples of %d (UNet pad path, blocks.py:225-229, not built yet)", H, W, div);
+    // UNet.forward pads its input (the conv_in output) at the bottom / right to multiples of 2^(levels-1) and crops its output
+    // back (blocks.py:225-229,245): conv_in and norm_out / conv_out run at H x W, everything between at Hp x Wp
+    const int Hp = (H + div - 1) / div * div, Wp = (W + div - 1) / div * div;
+    const bool padded = Hp != H || Wp != W;
+    if (padded && pl->train) return fail("denoiser: training at H=%d W=%d (not multiples of %d) needs the pad / crop adjoints, which are not built", H, W, div);
     // operand scratch pool: sized for the largest operand of the network (level 0, widest channel count)
     int cmax = 16;
     for (int i = 0; i < L; ++i) cmax = c.channels[i] > cmax ? c.channels[i] : cmax;
-    const size_t slot_bytes = (plc16_bytes(B, H, W, cmax) + 255) & ~(size_t)255;
+    const size_t slot_bytes = (plc16_bytes(B, Hp, Wp, cmax) + 255) & ~(size_t)255;
     for (int i = 0; i < kScratchSlots; ++i) pl->scratch[i] = (uint8_t*)bump->take(slot_bytes);
     pl->scratch_next = 0;
     pl->CP_in = h->conv_in.c0_store;
@@ -1035,11 +1057,16 @@ struct PlanBuilder {
     pl->cond = (float*)bump->take((size_t)B * c.cond_channels * 4);
     pl->film = (float*)bump->take((size_t)B * h->film_rows * 4);
     Tens xin{pl->xin, nullptr, pl->CP_in, H, W, 8};
-    Tens x = tensor(c.channels[0], H, W, true);
+    Tens x = tensor(c.channels[0], H, W, !padded);
     {
       Operand in = prep(xin, nullptr, 0, 0, nullptr, 0, 0, false, false, true);
-      conv(h->conv_in, in, false, 1, nullptr, x, true);
+      conv(h->conv_in, in, false, 1, nullptr, x, !padded);
       Rec rec; rec.kind = R_CONVIN; rec.cw = &h->conv_in; rec.x = xin; rec.o = x; rec.in1 = in; record(rec);
+    }
+    if (padded) {
+      Tens xp = tensor(c.channels[0], Hp, Wp, true);
+      resize(x, xp);
+      x = xp;
     }
     std::vector<std::vector<Tens>> d_outputs;
     for (int i = 0; i < L; ++i) {
@@ -1068,6 +1095,11 @@ struct PlanBuilder {
       const std::vector<Tens>& skip = d_outputs[L - 1 - m];  // reversed(d_outputs); block k uses skip[::-1][k]
       const int ns = (int)skip.size();
       for (size_t k = 0; k < h->u_blocks[m].size(); ++k) x = resblock(h->u_blocks[m][k], x, &skip[ns - 1 - (int)k]);
+    }
+    if (padded) {   // x[..., :h, :w]
+      Tens xc = tensor(x.C, H, W, true);
+      resize(x, xc);
+      x = xc;
     }
     pl->CF = c.img_channels;
     pl->fout = (float*)bump->take((size_t)B * H * W * pl->CF * 4);
@@ -1379,6 +1411,7 @@ int run_forward(dmd_denoiser* h, Plan& pl, const float* noisy, const float* sigm
       if (op.fused.film != nullptr && op.fused.film != film) { FusedParams fp = op.fused; fp.film = film; if (fused_launch(fp, op.smem, op.cols, st)) return 1; }
       else if (fused_launch(op.fused, op.smem, op.cols, st)) return 1;
     }
+    else if (op.kind == OP_RESIZE) { if (resize_launch(op.rs, st)) return 1; }
     else { if (attn_launch(op.attn, pl.B, st)) return 1; }
   }
   return 0;

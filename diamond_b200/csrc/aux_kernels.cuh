@@ -77,6 +77,24 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
   for (int ch = 0; ch < C; ++ch) out[((size_t)n * C + ch) * HW + pix] = i[ch];
 }
 
+// Zero-pad / crop of an NHWC fp32 tensor at the bottom / right edges (UNet.forward, blocks.py:225-229 `F.pad(x, (0, pw, 0, ph))` and
+// :245 `x[..., :h, :w]`): dst[n][y][x][:] = (y < Hs && x < Ws) ? src[n][y][x][:] : 0.  One float4 per thread; C % 4 == 0.
+struct ResizeParams { const float* src; float* dst; int B, Hs, Ws, Hd, Wd, C; double* stats; int gs; };
+__global__ void resize_nhwc_kernel(const ResizeParams p) {
+  const int C4 = p.C >> 2;
+  const long long total = (long long)p.B * p.Hd * p.Wd * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long r = i / C4;
+    const int x = (int)(r % p.Wd); r /= p.Wd;
+    const int y = (int)(r % p.Hd);
+    const int n = (int)(r / p.Hd);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < p.Hs && x < p.Ws) v = __ldg(reinterpret_cast<const float4*>(p.src + (((size_t)n * p.Hs + y) * p.Ws + x) * p.C) + c4);
+    reinterpret_cast<float4*>(p.dst)[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Conditioning path (inner_model.py:45, :27-35; blocks.py:84-87, :39,44), as one embedding kernel + three calls of a
 // small GEMM:   e = fourier(c_noise) + flatten(act_emb(act)) ;  h = silu(W0 e + b0) ;  cond = W1 h + b1 ;

@@ -33,6 +33,12 @@ CASES = {
         h=32, w=32, b=3, wseed=4321, iseed=78, sigmas=[0.05, 1.0, 12.0],
         sampler=O.SamplerCfg(num_steps_denoising=4, order=2, s_churn=1.0), rng_seed=5,
     ),
+    # UNet pad / crop path (blocks.py:225-229,245): 60 x 62 is not a multiple of 2^3, the U-Net runs at 64 x 64 on the
+    # zero-padded conv_in output and its result is cropped back before norm_out / conv_out
+    "denoiser_padded": dict(
+        inner=O.InnerCfg(), h=60, w=62, b=2, wseed=1357, iseed=79, sigmas=[0.4, 5.0],
+        sampler=O.SamplerCfg(num_steps_denoising=3), rng_seed=3,
+    ),
 }
 
 
@@ -51,11 +57,13 @@ def build_reference(ns, inner: O.InnerCfg, sd):
     return den.eval()
 
 
-def main():
+def main(only=None):
     ns = ref_import.load()
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         inner = c["inner"]
         sd = O.seeded_state_dict(O.inner_model_shapes(inner), c["wseed"])
         den = build_reference(ns, inner, sd)
@@ -274,6 +282,9 @@ def make_rew_end():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["inference", "training"]
+    named = [w for w in which if w in CASES]   # e.g. `python oracle/make_golden.py denoiser_padded`: only that fixture
+    if named:
+        main(named)
     if "inference" in which:
         main()
         make_actor_critic()

@@ -45,7 +45,7 @@ def _cases():
     return CASES
 
 
-@pytest.mark.parametrize("name", ["denoiser_default", "denoiser_small_heun"])
+@pytest.mark.parametrize("name", ["denoiser_default", "denoiser_small_heun", "denoiser_padded"])
 def test_denoiser_matches_reference_golden(golden_dir, name):
     dev = _dev()
     from oracle import torch_oracle as O
@@ -78,7 +78,7 @@ def test_denoiser_matches_reference_golden(golden_dir, name):
     assert _rel(mo2.cpu(), ref_mo) < REL_TOL
 
 
-@pytest.mark.parametrize("name", ["denoiser_default", "denoiser_small_heun"])
+@pytest.mark.parametrize("name", ["denoiser_default", "denoiser_small_heun", "denoiser_padded"])
 @pytest.mark.parametrize("graph", [False, True])
 def test_sampler_matches_reference_golden(golden_dir, name, graph):
     dev = _dev()
