@@ -395,7 +395,7 @@ def train_block(dev, world, rank, batch, steps=5, warmup=2):
     return {"workload": "Denoiser.forward + backward + gradient all-reduce + clip + AdamW (cfg 2), batch %d per GPU, 1 AR step" % batch,
             "value": batch * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "fwd_bwd_ms": tot[1] / steps,
             "allreduce_ms": tot[2] / steps, "clip_adamw_ms": tot[3] / steps, "collectives_per_step": ncoll if world > 1 else 0,
-            "allreduce_bytes": int(sum(p.numel() for p in den.parameters()) * 4), "loss": float(loss),
+            "allreduce_bytes": int(sum(p.numel() for p in den.parameters()) * 4), "loss": float(loss.detach()),
             "achieved_tflops_per_gpu": gflop / (tot[1] / steps), "steps": steps, "warmup": warmup}
 
 
@@ -471,7 +471,7 @@ def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1
     return {"workload": "ActorCritic.forward() over WorldModelEnv (%d envs x horizon %d, 3 denoise steps) + backward + clip + AdamW (cfg 3)" % (envs, horizon),
             "value": envs * horizon * world / (ms * 1e-3), "unit": "imagined frames/s (incl. policy update)", "ms_per_update": ms,
             "rollout_ms": tot[1] / updates, "backward_ms": tot[2] / updates, "allreduce_clip_adamw_ms": tot[3] / updates,
-            "loss": float(loss), "updates": updates, "warmup": warmup}
+            "loss": float(loss.detach()), "updates": updates, "warmup": warmup}
 
 
 def wgrad_roofline(dev, batch, peaks):
@@ -577,29 +577,11 @@ def run_native(args):
 
     dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms], dev)
     frames = B * args.steps * world
-    train = None
-    if not args.skip_train:
-        try:
-            train = train_block(dev, world, rank, args.train_batch)
-        except Exception as e:  # noqa: BLE001
-            train = {"error": repr(e)[:300]}
-    imag = None
-    if not args.skip_imagination:
-        try:
-            imag = imagination_block(dev, world, rank, envs=B)
-        except Exception as e:  # noqa: BLE001
-            imag = {"error": repr(e)[:300]}
+    line = None
     if rank == 0:
         peaks, peaks_src = load_peaks()
         roof = conv_roofline(dev, B, peaks, peaks_src)
         clocks = clk.finish()  # warm-up, both timed loops and the roofline loop are inside the sampling window
-        gpu_base = gpu_baseline(dev, B) if (world == 1 and not args.skip_gpu_baseline) else None
-        cpu_envs = 4
-        if world == 1 and not args.skip_cpu_baseline:
-            cores, avail = pick_cpu_threads()
-            cpu_val, cpu_times = cpu_frames_per_s(cpu_envs, 3, cores)
-        else:
-            cores, avail, cpu_val = 0, 0, None
         value = whole_job_value(B * args.steps, world, dev_ms)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -614,28 +596,59 @@ def run_native(args):
             "wall_s_timed_loop": t_wall,
             "parity": {"tolerance": "1e-3 RELATIVE L2 over the whole pre-quantisation model-output tensor vs the reference-pinned oracle "
                                     "(not max-per-element); outputs behind the truncating uint8 quantiser: never more than one level off",
-                       "tests": "tests/test_gpu_denoiser.py (B=1, 2, 3, 5 and the benchmarked B=32)"},
+                       "tests": "tests/test_gpu_denoiser.py (B=1, 2, 3, 5, the benchmarked B=32, and the padded 60x62 case)"},
         }
+    else:
+        clk.finish()
+
+    # The headline line is complete here.  The secondary blocks (cfg 2 training step, cfg 3 imagination update, the reference's GPU
+    # and CPU paths) run under a watchdog: if one of them hangs (a rank lost inside a collective, a compile that never returns) the
+    # line is printed without it and the process exits, instead of the run ending with no result.
+    def give_up(what):
+        if rank == 0 and line is not None:
+            line.setdefault("incomplete", []).append(what + ": watchdog timeout")
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    def guarded(what, seconds, fn):
+        timer = threading.Timer(seconds, give_up, args=(what,))
+        timer.daemon = True
+        timer.start()
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            return {"error": repr(e)[:300]}
+        finally:
+            timer.cancel()
+
+    train = guarded("train_denoiser", 240, lambda: train_block(dev, world, rank, args.train_batch)) if not args.skip_train else None
+    imag = guarded("imagination_update", 240, lambda: imagination_block(dev, world, rank, envs=B)) if not args.skip_imagination else None
+    if rank == 0:
         if train is not None:
             line["train_denoiser"] = train
-            try:
-                line["train_denoiser"]["wgrad_roofline"] = wgrad_roofline(dev, min(args.train_batch, 64), peaks)
-            except Exception as e:  # noqa: BLE001
-                line["train_denoiser"]["wgrad_roofline"] = {"error": repr(e)[:200]}
+            if "error" not in train:
+                line["train_denoiser"]["wgrad_roofline"] = guarded("wgrad_roofline", 60, lambda: wgrad_roofline(dev, min(args.train_batch, 64), peaks))
         if imag is not None:
             line["imagination_update"] = imag
-        if gpu_base is not None:
+        if world == 1 and not args.skip_gpu_baseline:
+            gpu_base = guarded("gpu_baseline", 300, lambda: gpu_baseline(dev, B))
             line["gpu_baseline"] = gpu_base
             for k in ("eager", "compiled_reduce_overhead"):
                 if gpu_base.get(k):
-                    line["gpu_baseline"]["e2e_speedup_vs_" + k] = line["e2e"]["value"] / gpu_base[k]
-        if cpu_val is not None:
-            line["cpu_baseline"] = {"value": cpu_val, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cpu_envs} envs x 3 sample() calls of the same workload (oracle port of the reference, torch CPU fp32, {cores} threads = fastest of 8/16/32/64/{avail} available)"}
-        print(json.dumps(line))
-    if rank != 0:
-        clk.finish()
+                    gpu_base["e2e_speedup_vs_" + k] = line["e2e"]["value"] / gpu_base[k]
+        if world == 1 and not args.skip_cpu_baseline:
+            def cpu_leg():
+                cores, avail = pick_cpu_threads()
+                cpu_envs = 4
+                cpu_val, _ = cpu_frames_per_s(cpu_envs, 3, cores)
+                return {"value": cpu_val, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"{cpu_envs} envs x 3 sample() calls of the same workload (oracle port of the reference, torch CPU fp32, {cores} threads = fastest of 8/16/32/64/{avail} available)"}
+            line["cpu_baseline"] = guarded("cpu_baseline", 300, cpu_leg)
+        print(json.dumps(line), flush=True)
     if world > 1:
+        watchdog = threading.Timer(60, lambda: os._exit(0))   # the line is out: never hang in teardown
+        watchdog.daemon = True
+        watchdog.start()
         dist.barrier()
         dist.destroy_process_group()
 

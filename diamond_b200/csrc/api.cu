@@ -476,7 +476,7 @@ static int wgrad_launch(const WgradLaunch& L, float* dW, cudaStream_t st) {
   WgradReduceParams rp = L.rp;
   rp.dW = dW;
   const int total = rp.n_mma * 2 * 64 * rp.N;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(rp);
+  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>(rp);
   DMD_LAUNCH_OK();
   return 0;
 }
@@ -1315,6 +1315,13 @@ struct BwdBuilder {
     };
     const float* Wf = h->packed ? (const float*)(h->packed + h->film_w_off) : nullptr;
     sgemm(pl->dfilm, R, 1, Wf, CC, 1, pl->dcond, -1, CC, B, CC, R, 0, 0);                       // dcond = dfilm Wf
+    {   // K = R (7168 rows for the default net) over a handful of 64 x 64 output tiles: split K across the SMs
+      int cmax = 16;
+      for (int i = 0; i < c.num_levels; ++i) cmax = c.channels[i] > cmax ? c.channels[i] : cmax;
+      long long fit = (long long)pl->H * pl->W * cmax / CC;   // partials live in tA (B * H * W * cmax floats)
+      int splits = R / 256; if (splits > 32) splits = 32; if (splits > fit) splits = (int)fit;
+      if (splits > 1) pl->bops.back().chunks = splits;
+    }
     sgemm(pl->dcond, 1, CC, pl->chid, CC, 1, nullptr, h->goff[h->i_cp2w], CC, CC, CC, B, 1, 1);  // dW2 += dcond^T h
     colsum(pl->dcond, B, CC, CC, h->i_cp2b);
     sgemm(pl->dcond, CC, 1, P(h->i_cp2w), CC, 1, pl->dh, -1, CC, B, CC, CC, 0, 0);               // dh = dcond W2
@@ -1602,6 +1609,17 @@ int run_backward(dmd_denoiser* h, Plan& pl, const float* grad_out, float* grads,
       case B_MEMSET: DMD_CUDA(cudaMemsetAsync(b.ms_ptr, 0, b.ms_bytes, st)); break;
       case B_SGEMM: {
         float* C = b.c_goff >= 0 ? grads + b.c_goff : b.gc;
+        if (b.chunks > 1) {   // long-K product (dcond = dfilm Wf, K = all FiLM rows): split-K partials in tA, fixed-order reduce
+          const int kchunk = ((b.K + b.chunks - 1) / b.chunks + 15) / 16 * 16;
+          const int splits = (b.K + kchunk - 1) / kchunk;
+          const long long count = (long long)b.M * b.N;
+          sgemm_kernel<<<dim3((b.N + 63) / 64, (b.M + 63) / 64, splits), 256, 0, st>>>(b.ga, b.sam, b.sak, b.gb, b.sbk, b.sbn, pl.tA, b.N, b.M, b.N, b.K, nullptr, 0, kchunk, count);
+          DMD_LAUNCH_OK();
+          if (b.ldc != b.N) return fail("backward: split-K sgemm needs a dense result");
+          splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(pl.tA, splits, count, C, b.use_inv ? inv : nullptr, b.acc);
+          DMD_LAUNCH_OK();
+          break;
+        }
         sgemm_kernel<<<dim3((b.N + 63) / 64, (b.M + 63) / 64), 256, 0, st>>>(b.ga, b.sam, b.sak, b.gb, b.sbk, b.sbn, C, b.ldc, b.M, b.N, b.K, b.use_inv ? inv : nullptr, b.acc);
         DMD_LAUNCH_OK();
         break;

@@ -289,12 +289,17 @@ __global__ void dsilu_mul_kernel(const float* __restrict__ pre, const float* __r
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sam, long long sak,
                                                     const float* __restrict__ Bm, long long sbk, long long sbn,
                                                     float* __restrict__ C, long long ldc, int M, int N, int K,
-                                                    const float* __restrict__ alpha_ptr, int accumulate) {
+                                                    const float* __restrict__ alpha_ptr, int accumulate,
+                                                    int kchunk = 0, long long c_split_stride = 0) {
   __shared__ float As[16][64 + 4], Bs[16][64 + 4];
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // split-K (gridDim.z > 1): block z multiplies the K range [z * kchunk, (z + 1) * kchunk) into its own partial C at
+  // C + z * c_split_stride; splitk_reduce_kernel then adds the partials in a fixed order (deterministic)
+  const int kbeg = kchunk > 0 ? blockIdx.z * kchunk : 0;
+  if (kchunk > 0) { K = min(K, kbeg + kchunk); C += (long long)blockIdx.z * c_split_stride; }
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
       // choose the fast index along the contiguous dimension of each operand
       int kk, mm;
@@ -329,6 +334,17 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
         *c = accumulate ? *c + v : v;
       }
     }
+}
+
+// out[i] (+)= alpha * sum_z partial[z][i], z ascending (the second half of a split-K sgemm)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long count, float* __restrict__ out,
+                                     const float* __restrict__ alpha_ptr, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(long long)z * count + i];
+  if (alpha_ptr) s *= *alpha_ptr;
+  out[i] = accumulate ? out[i] + s : s;
 }
 
 // FiLM weight gradients through a row-pointer table: the 44 AdaGroupNorm.linear layers (blocks.py:39) were batched into one

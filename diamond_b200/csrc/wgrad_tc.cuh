@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
 
 // Fixed-order reduction of the per-CTA partials into the torch-layout weight gradient [Cout][CinTot][taps] (fp32):
 //   dW[co][ci_off + ci][t] (+)= inv_scale * sum_part partial[part][i][h*64 + co][ci]      for (i, h) with tap(i, h) = t
-// inv_scale undoes the loss scaling of the gradient operand (device scalar).  One thread per (i, h, co, ci).
+// inv_scale undoes the loss scaling of the gradient operand (device scalar).
 struct WgradReduceParams {
   const float* partial; int nparts; int n_mma; int N;
   int tap_of[kWgMaxMma][2];     // tap index of (MMA i, row half h) or -1
@@ -188,22 +188,44 @@ struct WgradReduceParams {
   const float* inv_scale;       // device scalar or null (1.0)
   int accumulate;
 };
-__global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceParams p) {
+  // 64 consecutive outputs per block x 4 groups of partials: thread (kg, o) adds partials kg, kg + 4, ... of output o with four
+  // independent accumulators (the loads of one output are 196 KB apart: latency-bound unless many are in flight), then the four
+  // groups are combined through shared memory.  The order of every addition is fixed, so the result is deterministic.
+  __shared__ float part[4][64];
+  const int o = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + o;        // == offset of the element inside one CTA's partial block [n_mma][128][N]
   const int per = 2 * 64 * p.N;
-  if (idx >= p.n_mma * per) return;
-  const int i = idx / per, r = idx - i * per;
-  const int m = r / p.N, ci = r - m * p.N;
-  const int h = m >> 6, co = m & 63;
-  const int t = p.tap_of[i][h];
-  if (t < 0 || co >= p.Cout || ci >= p.Cin) return;
-  const size_t stride = (size_t)p.n_mma * kTileM * p.N;
-  const float* src = p.partial + ((size_t)i * kTileM + m) * p.N + ci;
+  int t = -1, co = 0, ci = 0;
+  if (idx < p.n_mma * per) {
+    const int i = idx / per, r = idx - i * per;
+    const int m = r / p.N;
+    ci = r - m * p.N;
+    co = m & 63;
+    t = p.tap_of[i][m >> 6];
+  }
+  const bool live = t >= 0 && co < p.Cout && ci < p.Cin;
   float s = 0.f;
-  for (int k = 0; k < p.nparts; ++k) s += src[(size_t)k * stride];
-  if (p.inv_scale) s *= *p.inv_scale;
-  float* d = p.dW + ((size_t)co * p.CinTot + p.ci_off + ci) * p.taps + t;
-  *d = p.accumulate ? *d + s : s;
+  if (live) {
+    const size_t stride = (size_t)p.n_mma * kTileM * p.N;
+    const float* src = p.partial + idx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = kg;
+    for (; k + 12 < p.nparts; k += 16) {
+      a0 += src[(size_t)k * stride]; a1 += src[(size_t)(k + 4) * stride];
+      a2 += src[(size_t)(k + 8) * stride]; a3 += src[(size_t)(k + 12) * stride];
+    }
+    for (; k < p.nparts; k += 4) a0 += src[(size_t)k * stride];
+    s = (a0 + a1) + (a2 + a3);
+  }
+  part[kg][o] = s;
+  __syncthreads();
+  if (kg == 0 && live) {
+    s = (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
+    if (p.inv_scale) s *= *p.inv_scale;
+    float* d = p.dW + ((size_t)co * p.CinTot + p.ci_off + ci) * p.taps + t;
+    *d = p.accumulate ? *d + s : s;
+  }
 }
 
 }  // namespace dmd
