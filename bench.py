@@ -414,7 +414,7 @@ def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1
     from diamond_b200.models.diffusion import Denoiser, DenoiserConfig, DiffusionSamplerConfig, InnerModelConfig
     from diamond_b200.models.rew_end_model import RewEndModel, RewEndModelConfig
     from diamond_b200.synthetic import frame_stacks, randomize_module_
-    from diamond_b200.utils import allreduce_gradients
+    from diamond_b200.utils import allreduce_native_gradients
 
     den = Denoiser(DenoiserConfig(InnerModelConfig(3, 4, 256, [2, 2, 2, 2], [64] * 4, [0] * 4, 4), 0.5, 0.3))
     randomize_module_(den.inner_model, 2024)
@@ -459,7 +459,7 @@ def imagination_block(dev, world, rank, envs=32, horizon=15, updates=3, warmup=1
         e1.record()
         loss.backward()
         e2.record()
-        allreduce_gradients(list(ac.parameters()))
+        allreduce_native_gradients(ac)   # the BPTT nodes accumulated into ONE flat buffer: one collective
         torch.nn.utils.clip_grad_norm_(ac.parameters(), 100.0)
         opt.step()
         e3.record()

@@ -114,6 +114,7 @@ SIGNATURES = {
     "dmd_actor_critic_backward_scratch_bytes": (_sz, [_vp, _i]),
     "dmd_actor_critic_grad_layout": (C.c_longlong, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
     "dmd_actor_critic_backward": (_i, [_vp, _i] + [_vp] * 8 + [C.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmd_actor_critic_backward_accumulate": (_i, [_vp, _i] + [_vp] * 8 + [C.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmd_rew_end_create": (_vp, [C.POINTER(RewEndConfigC)]),
     "dmd_rew_end_destroy": (None, [_vp]),
     "dmd_rew_end_num_tensors": (_i, [_vp]),

@@ -2073,10 +2073,27 @@ extern "C" long long dmd_actor_critic_grad_layout(const dmd_actor_critic* h, lon
   return h->grad_total;
 }
 
+static int ac_backward_impl(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                            const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
+                            float* grads, long long grads_numel, int accumulate, float* g_hx_in, float* g_cx_in, void* workspace,
+                            void* scratch, size_t scratch_bytes, void* stream);
 extern "C" int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
                                          const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
                                          float* grads, long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace,
                                          void* scratch, size_t scratch_bytes, void* stream) {
+  return ac_backward_impl(h, B, hx_in, cx_in, hx_out, g_logits, g_val, g_hx, g_cx, grads, grads_numel, 0, g_hx_in, g_cx_in, workspace, scratch, scratch_bytes, stream);
+}
+extern "C" int dmd_actor_critic_backward_accumulate(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                                                    const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
+                                                    float* grads, long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace,
+                                                    void* scratch, size_t scratch_bytes, void* stream) {
+  return ac_backward_impl(h, B, hx_in, cx_in, hx_out, g_logits, g_val, g_hx, g_cx, grads, grads_numel, 1, g_hx_in, g_cx_in, workspace, scratch, scratch_bytes, stream);
+}
+// every parameter-gradient writer below ADDS its (un-scaled) contribution, so "accumulate" is simply "do not clear the buffer first"
+static int ac_backward_impl(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                            const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
+                            float* grads, long long grads_numel, int accumulate, float* g_hx_in, float* g_cx_in, void* workspace,
+                            void* scratch, size_t scratch_bytes, void* stream) {
   DMD_CHECK(h && hx_in && cx_in && hx_out && grads && g_hx_in && g_cx_in && workspace && scratch, "ac backward: null argument");
   DMD_CHECK(!h->ptrs.empty() && h->packed, "ac backward: call dmd_actor_critic_set_weights first");
   DMD_CHECK(grads_numel >= h->grad_total && ((uintptr_t)grads & 15) == 0, "ac backward: bad gradient buffer");
@@ -2102,7 +2119,7 @@ extern "C" int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float
     DMD_LAUNCH_OK();
     return 0;
   };
-  DMD_CUDA(cudaMemsetAsync(grads, 0, (size_t)h->grad_total * 4, st));
+  if (!accumulate) DMD_CUDA(cudaMemsetAsync(grads, 0, (size_t)h->grad_total * 4, st));
   DMD_CUDA(cudaMemsetAsync(sc.amax, 0, 256, st));
   // ---- heads (actor_critic.py:73)
   heads_bwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(g_hx, g_logits, g_val, h->ptrs[h->i_aw], h->ptrs[h->i_cw], sc.g_h, B, D, A);

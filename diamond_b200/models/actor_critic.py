@@ -66,6 +66,9 @@ class ActorCritic(NativeStateMixin, nn.Module):
         init_lstm(self.lstm)
         self.env_loop = None
         self.loss_cfg = None
+        # True: the nodes of a backward pass accumulate their parameter gradients natively and `.grad` is set when the pass ends
+        # (what `loss.backward()` needs).  False: every node returns its gradients to autograd (needed for torch.autograd.grad).
+        self.accumulate_native_grads = True
         self._h = None
         self._h_dev = None
         self._wkey = None
@@ -94,6 +97,7 @@ class ActorCritic(NativeStateMixin, nn.Module):
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("diamond_b200 runs on CUDA (sm_100a) only; move the model to a cuda device")
+        self.require_current_device(dev)
         if self._h is None:
             c = self.cfg
             cc = _lib.ActorCriticConfigC()
@@ -127,6 +131,34 @@ class ActorCritic(NativeStateMixin, nn.Module):
         if total < 0:
             raise RuntimeError("diamond_b200: " + lib.dmd_last_error().decode())
         return list(offs), list(nums), int(total)
+
+    def _grad_views_layout(self):
+        """(offsets, numels) of every PARAMETER (in `parameters()` order) inside the flat gradient buffer, and its length.
+        Static for a module, so it is computed once (walking state_dict() costs ~0.2 ms, and there are ~60 backward nodes per update)."""
+        cached = self.__dict__.get("_gv_layout")
+        if cached is None:
+            offs, nums, total = self.grad_layout()
+            index = {k: i for i, k in enumerate(self.state_dict().keys())}
+            names = [k for k, _ in self.named_parameters()]
+            cached = self.__dict__["_gv_layout"] = ([offs[index[k]] for k in names], [nums[index[k]] for k in names], total)
+        return cached
+
+    def _adopt_accumulated_grads(self) -> None:
+        """End of a backward pass (autograd engine callback): the flat buffer the BPTT nodes accumulated into becomes `.grad`
+        (added to an existing `.grad`, like AccumulateGrad) and is remembered as `last_flat_grad` for a one-collective all-reduce."""
+        flat = self.__dict__.pop("_grad_acc", None)
+        if flat is None:
+            return
+        offs, nums, _ = self._grad_views_layout()
+        for p, o, n in zip(self.parameters(), offs, nums):
+            if not p.requires_grad:
+                continue
+            g = flat[o:o + n].view_as(p)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+        self.last_flat_grad = flat
 
     def _acquire_ws(self, nbytes: int, dev) -> Tensor:
         pool = self.__dict__.setdefault("_ws_pool", [])
@@ -173,6 +205,7 @@ class ActorCritic(NativeStateMixin, nn.Module):
     def forward(self) -> LossAndLogs:  # actor_critic.py:75-98
         """REINFORCE with a lambda-return baseline over one imagined rollout of `backup_every` steps."""
         cfg = self.loss_cfg
+        self.__dict__.pop("_grad_acc", None)   # a backward pass that died half-way must not leak into this update
         _, act, rew, end, trunc, logits, val, val_bootstrap, _ = self.env_loop.send(cfg.backup_every)
         policy = Categorical(logits=logits, validate_args=False)
         entropy = policy.entropy().mean()
@@ -238,8 +271,7 @@ class _PredictActValueFn(torch.autograd.Function):
         h = module._native()
         hx, cx, hx_o = ctx.saved_tensors
         dev = hx.device
-        offs, nums, total = module.grad_layout()
-        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        offs, nums, total = module._grad_views_layout()
         g_hx_in, g_cx_in = torch.empty_like(hx), torch.empty_like(cx)
         need = lib.dmd_actor_critic_backward_scratch_bytes(h, ctx.b)
         scratch = module.__dict__.get("_bwd_scratch")
@@ -250,14 +282,23 @@ class _PredictActValueFn(torch.autograd.Function):
             return None if t is None else t.float().contiguous()
 
         gl, gv, gh, gc = c(g_logits), c(g_val), c(g_hx), c(g_cx)
-        _lib.check(lib.dmd_actor_critic_backward(h, ctx.b, hx.data_ptr(), cx.data_ptr(), hx_o.data_ptr(), _lib.ptr(gl), _lib.ptr(gv),
-                                                 _lib.ptr(gh), _lib.ptr(gc), flat.data_ptr(), total, g_hx_in.data_ptr(),
-                                                 g_cx_in.data_ptr(), ctx.ws.data_ptr(), scratch.data_ptr(), scratch.numel(),
-                                                 _lib.current_stream()))
+        args = (h, ctx.b, hx.data_ptr(), cx.data_ptr(), hx_o.data_ptr(), _lib.ptr(gl), _lib.ptr(gv), _lib.ptr(gh), _lib.ptr(gc))
+        tail = (g_hx_in.data_ptr(), g_cx_in.data_ptr(), ctx.ws.data_ptr(), scratch.data_ptr(), scratch.numel(), _lib.current_stream())
+        if module.accumulate_native_grads:
+            # One flat gradient buffer per backward pass: every node of the BPTT graph ADDS into it natively, and a callback that the
+            # autograd engine runs once the pass is complete hands it to the parameters.  (Returning ~40 gradient views per node
+            # instead makes autograd's AccumulateGrad launch ~40 tiny additions for each of the ~60 nodes of a rollout.)
+            flat = module.__dict__.get("_grad_acc")
+            if flat is None:
+                flat = module.__dict__["_grad_acc"] = torch.empty(total, dtype=torch.float32, device=dev)
+                _lib.check(lib.dmd_actor_critic_backward(*args, flat.data_ptr(), total, *tail))
+                torch.autograd.Variable._execution_engine.queue_callback(module._adopt_accumulated_grads)
+            else:
+                _lib.check(lib.dmd_actor_critic_backward_accumulate(*args, flat.data_ptr(), total, *tail))
+            module._release_ws(ctx.ws)
+            return (None, None, g_hx_in, g_cx_in, *([None] * len(offs)))
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        _lib.check(lib.dmd_actor_critic_backward(*args, flat.data_ptr(), total, *tail))
         module._release_ws(ctx.ws)
-        index = {k: i for i, k in enumerate(module.state_dict().keys())}
-        grads = []
-        for name, p in module.named_parameters():
-            i = index[name]
-            grads.append(flat[offs[i]:offs[i] + nums[i]].view_as(p))
+        grads = [flat[o:o + n].view_as(p) for (o, n), p in zip(zip(offs, nums), module.parameters())]
         return (None, None, g_hx_in, g_cx_in, *grads)

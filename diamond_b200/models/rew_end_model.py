@@ -76,6 +76,7 @@ class RewEndModel(NativeStateMixin, nn.Module):
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("diamond_b200 runs on CUDA (sm_100a) only; move the model to a cuda device")
+        self.require_current_device(dev)
         if self._h is None or self._h_dev != dev.index:
             if self._h is not None:
                 lib.dmd_rew_end_destroy(self._h)

@@ -43,6 +43,31 @@ class NativeStateMixin:
         self.__dict__["_state_tensor_cache"] = None
         return super()._apply(fn, recurse)
 
+    # The native handle (`_h`, a raw pointer owned by __del__), the packed fp16 weights, workspaces and cached layouts belong
+    # to ONE module object.  copy.deepcopy (EMA copies) and pickle (multiprocessing) go through __getstate__: the copy starts
+    # without native state and builds its own on first use, so two objects never own -- and free -- the same handle.
+    _NATIVE_RESET = ("_h", "_h_key", "_h_dev", "_wkey", "_packed", "_ws")
+    _NATIVE_DROP = ("_state_tensor_cache", "_tws_pool", "_ws_pool", "_bwd_scratch", "_grad_acc", "_gv_layout", "last_flat_grad")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in self._NATIVE_RESET:
+            if k in state:
+                state[k] = None
+        for k in self._NATIVE_DROP:
+            state.pop(k, None)
+        return state
+
+    @staticmethod
+    def require_current_device(dev) -> None:
+        """The native layer launches on the CURRENT CUDA device and on its current stream; a model that lives on another device
+        would silently run on the wrong GPU.  Fail loudly instead (the reference trainer calls torch.cuda.set_device, trainer.py:52)."""
+        import torch
+
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            raise RuntimeError(f"diamond_b200: the module is on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               f"call torch.cuda.set_device({dev.index}) (or wrap the call in torch.cuda.device) first")
+
 
 # ----------------------------------------------------------------------------------------------- data-parallel plumbing
 # SURVEY.md 8 a26.  The reference wraps each agent module in torch DDP (utils.py:105-106, trainer.py:110) and relies on

@@ -291,6 +291,12 @@ int dmd_actor_critic_backward(dmd_actor_critic* h, int B, const float* hx_in, co
                               const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx, float* grads,
                               long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace, void* scratch,
                               size_t scratch_bytes, void* stream);
+/* Same, but ADDS the parameter gradients to what `grads` already holds: the nodes of one back-propagation-through-time pass
+ * accumulate into one flat buffer (what autograd's AccumulateGrad does tensor by tensor in the reference, trainer.py:366). */
+int dmd_actor_critic_backward_accumulate(dmd_actor_critic* h, int B, const float* hx_in, const float* cx_in, const float* hx_out,
+                                         const float* g_logits, const float* g_val, const float* g_hx, const float* g_cx,
+                                         float* grads, long long grads_numel, float* g_hx_in, float* g_cx_in, void* workspace,
+                                         void* scratch, size_t scratch_bytes, void* stream);
 
 /* compute_lambda_returns (src/models/actor_critic.py:116-143): rew / val_bootstrap fp32 [B][T], end / trunc int64 [B][T] ->
  * out fp32 [B][T]; one thread per environment walks time backwards; bit-identical to the reference's torch expression. */

@@ -89,3 +89,33 @@ def test_synthetic_generators_match_the_oracle_rule():
     obs, act, x0 = frame_stacks(3, 4, 3, 64, 64, 4, 7)
     o2, a2, x2 = O.synthetic_inputs(3, inner, 64, 64, 7)
     assert torch.equal(obs, o2) and torch.equal(act, a2) and torch.equal(x0, x2)
+
+
+def test_copies_of_a_native_module_do_not_share_the_native_handle():
+    """copy.deepcopy / pickle of a module with a native executor (EMA copies, multiprocessing): the copy must start without
+    the raw handle, the packed weights and the cached layouts of the original (a shared handle would be freed twice)."""
+    import copy
+    import pickle
+
+    from diamond_b200.models.actor_critic import ActorCritic, ActorCriticConfig
+    from diamond_b200.models.diffusion import InnerModelConfig
+    from diamond_b200.models.diffusion.inner_model import InnerModel
+
+    im = InnerModel(InnerModelConfig(3, 2, 64, [1, 1], [32, 32], [0, 0], 4))
+    ac = ActorCritic(ActorCriticConfig(64, 3, 16, [32, 32], [1, 1], 4))
+    for m in (im, ac):
+        m._state_tensors()
+        m.__dict__["_h"] = 0xDEAD           # stands in for a live native handle (never dereferenced on this CPU box)
+        m.__dict__["_wkey"] = ("stale",)
+        m.__dict__["_packed"] = torch.zeros(4)
+        m.__dict__["_ws_pool"] = [torch.zeros(1)]
+        m.__dict__["_gv_layout"] = ([0], [1], 1)
+        try:
+            for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+                assert clone._h is None and clone._wkey is None and clone._packed is None
+                assert "_ws_pool" not in clone.__dict__ and "_gv_layout" not in clone.__dict__ and "_state_tensor_cache" not in clone.__dict__
+                assert list(clone.state_dict().keys()) == list(m.state_dict().keys())
+                assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
+            assert m._h == 0xDEAD and m._wkey == ("stale",)   # the original keeps its own state
+        finally:
+            m.__dict__["_h"] = None         # __del__ must not hand the fake handle to the library
