@@ -3,7 +3,12 @@
 
 A "step" = one DiffusionSampler.sample() call over a batch of `--envs` imagined environments per GPU
 (frame-stack 4 x 64x64x3 fp32 + 4 actions -> next frame, 3 Euler denoising steps = 3 U-Net forwards).
-Multi-GPU is weak scaling with no data-path collective (imagination needs no communication).
+`value` is device-resident throughput, `e2e` the same call with pinned HOST buffers in and out, `roofline` the dominant conv
+kernel timed alone.  Secondary blocks on the same line (each under a watchdog, so the headline line is always printed):
+`train_denoiser` (cfg 2: Denoiser.forward + backward + ONE flat-buffer NCCL all-reduce + clip + AdamW, + the wgrad kernel's
+roofline), `imagination_update` (cfg 3: 32 envs x horizon 15 through WorldModelEnv + policy BPTT + all-reduce + AdamW),
+`gpu_baseline` (the reference's GPU path on this GPU: eager and torch.compile), `cpu_baseline` (its CPU path on the host cores).
+Multi-GPU is weak scaling: imagination needs no collective; both training blocks all-reduce their gradients.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--impl native|reference]
 
