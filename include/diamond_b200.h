@@ -199,6 +199,9 @@ size_t dmd_denoiser_packed_bytes(const dmd_denoiser* h);
  * Re-packs the tensor-core copies; call again after every optimizer step / load_state_dict. */
 int dmd_denoiser_set_weights(dmd_denoiser* h, const float* const* ptrs_host, int n_ptrs, void* packed, void* stream);
 
+/* H, W need not be multiples of 2^(levels-1): like UNet.forward (blocks.py:225-229,245) the executor zero-pads the conv_in
+ * output at the bottom / right, runs the U-Net on the padded size and crops before norm_out / conv_out (inference entry
+ * points; the training entry points reject such sizes).  The deepest level must hold 64 positions when it has attention. */
 size_t dmd_denoiser_workspace_bytes(const dmd_denoiser* h, int B, int H, int W);
 
 /* One Denoiser.denoise / compute_model_output call.  noisy (B,C,H,W), sigma (B) or (1), obs (B,T*C,H,W),
