@@ -91,3 +91,49 @@ def test_allreduce_gradients_is_a_noop_without_a_process_group():
     before = lin.weight.grad.clone()
     assert allreduce_gradients(list(lin.parameters())) == 0
     assert torch.equal(before, lin.weight.grad)
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diamond_b200.utils import allreduce_native_gradients
+
+    class Model(torch.nn.Module):   # what a native backward leaves behind: every .grad is a view of ONE flat buffer
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.zeros(3, 4))
+            self.b = torch.nn.Parameter(torch.zeros(5))
+            self.frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+
+    m = Model()
+    flat = torch.arange(17, dtype=torch.float32) * (rank + 1)        # rank-dependent gradients
+    m.a.grad, m.b.grad = flat[0:12].view(3, 4), flat[12:17]
+    m.last_flat_grad = flat
+    calls_aliased = allreduce_native_gradients(m)
+    want = torch.arange(17, dtype=torch.float32) * (sum(r + 1 for r in range(world)) / world)
+    ok_aliased = torch.equal(flat, want) and torch.equal(m.a.grad.reshape(-1), want[:12]) and m.a.grad.data_ptr() == flat.data_ptr()
+    # gradients that no longer alias the buffer (e.g. after gradient accumulation): bucketed fallback, same average
+    m.a.grad = (torch.ones(3, 4) * (rank + 1)).clone()
+    calls_fallback = allreduce_native_gradients(m)
+    ok_fallback = torch.allclose(m.a.grad, torch.full((3, 4), sum(r + 1 for r in range(world)) / world)) and torch.allclose(m.b.grad, want[12:] * 1.0)
+    q.put((rank, calls_aliased, ok_aliased, calls_fallback, ok_fallback))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_buffer_allreduce_is_one_collective():
+    """the training blocks of bench.py average a model's gradients with ONE all_reduce on the flat buffer the
+    native backward filled (`allreduce_native_gradients`); when `.grad`s do not alias that buffer it falls back to buckets."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls_aliased, ok_aliased, calls_fallback, ok_fallback in out:
+        assert calls_aliased == 1 and ok_aliased
+        assert calls_fallback >= 1 and ok_fallback
