@@ -6,7 +6,6 @@ nn.Linear / nn.GroupNorm).  They do NOT compute anything in PyTorch: the arithme
 native executor (diamond_b200/csrc), which reads these tensors through their device pointers.  Calling a container
 directly raises, so an accidental eager path cannot hide behind the CUDA one.
 """
-import math
 from typing import List
 
 import torch

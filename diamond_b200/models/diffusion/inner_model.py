@@ -1,7 +1,7 @@
 """InnerModel (reference: src/models/diffusion/inner_model.py) bound to the native denoiser executor."""
 import ctypes as C
 from dataclasses import dataclass
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 from torch import Tensor
