@@ -506,6 +506,38 @@ def wgrad_roofline(dev, batch, peaks):
             "achieved": flops / (us * 1e-6) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (us * 1e-6) / 1e12 / peak}
 
 
+class SecondaryBlocks:
+    """Runs the optional blocks of the bench line after the headline numbers exist.  Every block gets a watchdog (its own limit,
+    clipped to what is left of a budget shared by all blocks); when a watchdog fires, rank 0 prints the line as far as it got --
+    tagged in `incomplete` -- and the process exits 0.  A block whose turn comes after the budget is spent is skipped."""
+
+    def __init__(self, rank: int, line, budget_s: float, exit_fn=os._exit, out=None):
+        self.rank, self.line, self.exit_fn, self.out = rank, line, exit_fn, out
+        self.deadline = time.monotonic() + budget_s
+
+    def _give_up(self, what: str) -> None:
+        if self.rank == 0 and self.line is not None:
+            self.line.setdefault("incomplete", []).append(what + ": watchdog timeout")
+            print(json.dumps(self.line), file=self.out or sys.stdout, flush=True)
+        self.exit_fn(0)
+
+    def run(self, what: str, seconds: float, fn):
+        left = self.deadline - time.monotonic()
+        if left < 3.0:
+            if self.rank == 0 and self.line is not None:
+                self.line.setdefault("incomplete", []).append(what + ": skipped, secondary time budget spent")
+            return {"skipped": "secondary time budget spent"}
+        timer = threading.Timer(min(seconds, left), self._give_up, args=(what,))
+        timer.daemon = True
+        timer.start()
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            return {"error": repr(e)[:300]}
+        finally:
+            timer.cancel()
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -607,40 +639,19 @@ def run_native(args):
         clk.finish()
 
     # The headline line is complete here.  The secondary blocks (cfg 2 training step, cfg 3 imagination update, the reference's GPU
-    # and CPU paths) run under a watchdog: if one of them hangs (a rank lost inside a collective, a compile that never returns) the
-    # line is printed without it and the process exits, instead of the run ending with no result.
-    def give_up(what):
-        if rank == 0 and line is not None:
-            line.setdefault("incomplete", []).append(what + ": watchdog timeout")
-            print(json.dumps(line), flush=True)
-        os._exit(0)
-
-    def guarded(what, seconds, fn):
-        timer = threading.Timer(seconds, give_up, args=(what,))
-        timer.daemon = True
-        timer.start()
-        try:
-            return fn()
-        except Exception as e:  # noqa: BLE001
-            return {"error": repr(e)[:300]}
-        finally:
-            timer.cancel()
+    # and CPU paths) run under a watchdog and a shared time budget: if one of them hangs (a rank lost inside a collective, a compile
+    # that never returns) or the host is slow, the line is printed without it instead of the run ending with no result.
+    guarded = SecondaryBlocks(rank, line, args.secondary_budget).run
 
     train = guarded("train_denoiser", 240, lambda: train_block(dev, world, rank, args.train_batch)) if not args.skip_train else None
     imag = guarded("imagination_update", 240, lambda: imagination_block(dev, world, rank, envs=B)) if not args.skip_imagination else None
     if rank == 0:
         if train is not None:
             line["train_denoiser"] = train
-            if "error" not in train:
+            if "error" not in train and "skipped" not in train:
                 line["train_denoiser"]["wgrad_roofline"] = guarded("wgrad_roofline", 60, lambda: wgrad_roofline(dev, min(args.train_batch, 64), peaks))
         if imag is not None:
             line["imagination_update"] = imag
-        if world == 1 and not args.skip_gpu_baseline:
-            gpu_base = guarded("gpu_baseline", 300, lambda: gpu_baseline(dev, B))
-            line["gpu_baseline"] = gpu_base
-            for k in ("eager", "compiled_reduce_overhead"):
-                if gpu_base.get(k):
-                    gpu_base["e2e_speedup_vs_" + k] = line["e2e"]["value"] / gpu_base[k]
         if world == 1 and not args.skip_cpu_baseline:
             def cpu_leg():
                 cores, avail = pick_cpu_threads()
@@ -649,6 +660,12 @@ def run_native(args):
                 return {"value": cpu_val, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"{cpu_envs} envs x 3 sample() calls of the same workload (oracle port of the reference, torch CPU fp32, {cores} threads = fastest of 8/16/32/64/{avail} available)"}
             line["cpu_baseline"] = guarded("cpu_baseline", 300, cpu_leg)
+        if world == 1 and not args.skip_gpu_baseline:
+            gpu_base = guarded("gpu_baseline", 300, lambda: gpu_baseline(dev, B))
+            line["gpu_baseline"] = gpu_base
+            for k in ("eager", "compiled_reduce_overhead"):
+                if gpu_base.get(k):
+                    gpu_base["e2e_speedup_vs_" + k] = line["e2e"]["value"] / gpu_base[k]
         print(json.dumps(line), flush=True)
     if world > 1:
         watchdog = threading.Timer(60, lambda: os._exit(0))   # the line is out: never hang in teardown
@@ -670,6 +687,7 @@ def main():
     ap.add_argument("--skip-train", action="store_true", help="omit the denoiser-training block (cfg 2)")
     ap.add_argument("--train-batch", type=int, default=256, help="denoiser training batch per GPU (config/trainer.yaml: 32; BASELINE cfg 2: 256)")
     ap.add_argument("--skip-gpu-baseline", action="store_true", help="omit the reference-GPU-path leg (eager + torch.compile of the oracle port)")
+    ap.add_argument("--secondary-budget", type=float, default=200.0, help="seconds shared by the blocks that follow the headline numbers (training, imagination, baselines); ~55 s are used on a healthy box")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
