@@ -256,6 +256,11 @@ def conv_roofline(dev, envs, peaks, peaks_src):
     peak = float(peaks.get("bf16_tflops", 1590.0))
     return {"bound": "tensor", "kernel": ("conv_tc_kernel<256,3> (tap-row-stacked: 3 MMAs of N=192 per slab)" if TRS else "conv_tc_kernel<64,0> (tap-major: 9 MMAs of N=64 per slab)") + " 3x3 64->64 @64x64 on a PLC16 fp16 operand, bias + GroupNorm-stats epilogue",
             "prep_us_per_launch": ms_prep * 1e3,
+            # the operand pass that precedes every conv (GroupNorm / FiLM / SiLU -> fp16 PLC16): HBM-bound; algorithmic bytes =
+            # 256 B read (fp32 NHWC, 64 channels) + 128 B written per pixel
+            "prep": {"bound": "hbm", "kernel": "prep_fast_kernel<8,0>", "achieved": (256.0 + 128.0) * 4096.0 * envs / (ms_prep * 1e-3) / 1e9,
+                     "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                     "frac": (256.0 + 128.0) * 4096.0 * envs / (ms_prep * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))},
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": (128 * 1.0 + 256) * 4096.0 * envs,
             "us_per_launch": ms * 1e3, "flop_per_launch": flops, "peak_source": peaks_src + " bf16 burst (fp16 and bf16 share the tensor-pipe rate)"}
