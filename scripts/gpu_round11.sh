@@ -24,5 +24,5 @@ stamp bench
 run 120 python bench.py --impl reference > ${out}_bench_ref.json 2> ${out}_bench_ref.err; echo "ref rc=$?"; head -c 400 ${out}_bench_ref.json; echo; stamp ref
 run 120 ncu --clock-control none --set full --import-source on -k regex:'wgrad_tc_kernel|wgrad_reduce' --launch-skip 4 -c 4 -o ${out}_wgrad -f python scripts/prof_wgrad.py 64 > ${out}_ncu_wgrad.log 2>&1; tail -1 ${out}_ncu_wgrad.log; stamp ncu-wgrad
 run 150 ncu --clock-control none --metrics gpu__time_duration.sum -c 2500 --csv --log-file ${out}_launches_train.csv python scripts/prof_train.py 64 > ${out}_launches_train.log 2>&1; wc -l ${out}_launches_train.csv; stamp train-launches
-PYTHONUNBUFFERED=1 run 170 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 5 python -m pytest tests/test_gpu_denoiser.py tests/test_gpu_training.py -q -m gpu -p no:cacheprovider -k "(padded and reference_golden and not sampler) or accumulation_modes or optimizer" > ${out}_memcheck.log 2>&1
+PYTHONUNBUFFERED=1 run 170 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 5 python -m pytest tests/test_gpu_denoiser.py tests/test_gpu_training.py -q -m gpu -p no:cacheprovider -k "(padded and reference_golden and not sampler) or optimizer" > ${out}_memcheck.log 2>&1
 echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" ${out}_memcheck.log | tail -5; stamp memcheck

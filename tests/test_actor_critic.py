@@ -78,3 +78,40 @@ def test_native_actor_critic_matches_reference_golden(golden_dir):
         full = ac.predict_act_value(obs[0].to(dev), (hx, cx))
         part = ac.predict_act_value(obs[0][1:3].to(dev), (hx[1:3], cx[1:3]))
     assert torch.allclose(full.logits_act[1:3], part.logits_act, atol=1e-5)
+
+
+def test_accumulated_native_gradients_are_adopted_like_accumulate_grad():
+    """Host half of the BPTT gradient path (CPU): the flat buffer the native backward nodes accumulated into becomes `.grad` of
+    every trainable parameter as a VIEW (so one all-reduce on the buffer averages the model), frozen parameters are skipped, and
+    a second backward pass ADDS to the existing `.grad` (what autograd's AccumulateGrad does).  The native half (the nodes adding
+    into the buffer) is exercised on the GPU by tests/test_gpu_training.py::test_actor_critic_training_step_matches_reference."""
+    from diamond_b200.models.actor_critic import ActorCritic, ActorCriticConfig
+
+    ac = ActorCritic(ActorCriticConfig(64, 3, 16, [32, 32], [1, 1], 4))
+    names = list(ac.state_dict().keys())
+    sizes = [v.numel() for v in ac.state_dict().values()]
+    offs, o = [], 0
+    for n in sizes:                      # the layout dmd_actor_critic_grad_layout reports: state_dict order, 16-byte aligned slices
+        offs.append(o)
+        o += (n + 3) // 4 * 4
+    ac.grad_layout = lambda: (offs, sizes, o)          # stands in for the C-ABI query (needs the CUDA library)
+    frozen = next(iter(ac.parameters()))
+    frozen.requires_grad_(False)
+    flat = torch.arange(o, dtype=torch.float32)
+    ac.__dict__["_grad_acc"] = flat
+    ac._adopt_accumulated_grads()
+    assert "_grad_acc" not in ac.__dict__ and ac.last_flat_grad is flat
+    index = {k: i for i, k in enumerate(names)}
+    for k, p in ac.named_parameters():
+        if p is frozen:
+            assert p.grad is None
+            continue
+        want = flat[offs[index[k]]:offs[index[k]] + sizes[index[k]]].view_as(p)
+        assert torch.equal(p.grad, want) and p.grad.data_ptr() == want.data_ptr()
+    first = {k: p.grad.clone() for k, p in ac.named_parameters() if p.grad is not None}
+    ac.__dict__["_grad_acc"] = torch.ones(o)
+    ac._adopt_accumulated_grads()
+    for k, p in ac.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, first[k] + 1)
+    ac._adopt_accumulated_grads()        # nothing pending: a no-op
