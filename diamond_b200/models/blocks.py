@@ -33,12 +33,20 @@ class _NativeOnly(nn.Module):
 
 
 class GroupNorm(_NativeOnly):  # blocks.py:24-31
+    """Affine GroupNorm (groups of 32 channels).  Executed as: (sum, sumsq) per (image, group) from the PRODUCER's conv epilogue
+    (fp64 atomics), apply + SiLU inside the consumer's operand pass (`prep_fast_kernel` mode 2); backward = `norm_bwd_pass1/2`."""
+
     def __init__(self, in_channels: int) -> None:
         super().__init__()
         self.norm = nn.GroupNorm(max(1, in_channels // GN_GROUP_SIZE), in_channels, eps=GN_EPS)
 
 
 class AdaGroupNorm(_NativeOnly):  # blocks.py:34-45
+    """GroupNorm without affine + FiLM (1 + scale, shift) from the conditioning vector.  All AdaGroupNorm.linear layers of a network are
+    packed into ONE [sum 2C, cond] matrix and evaluated by a single GEMM per forward (`linear_kernel`), for every denoising step up
+    front in the sampler; the apply runs in the operand pass (mode 1).  Backward: `film_wgrad_kernel` scatters the batched gradient
+    back to the individual `linear.weight` / `linear.bias` slices of the flat gradient buffer."""
+
     def __init__(self, in_channels: int, cond_channels: int) -> None:
         super().__init__()
         self.in_channels = in_channels
@@ -47,6 +55,9 @@ class AdaGroupNorm(_NativeOnly):  # blocks.py:34-45
 
 
 class SelfAttention2d(_NativeOnly):  # blocks.py:51-72
+    """Multi-head self-attention over the H*W positions (head_dim 8) with a residual connection.  Executed by `attn_cluster_kernel`
+    (a 4-CTA cluster per image exchanging K / V through distributed shared memory; 64 positions) and `attn_bwd_kernel`."""
+
     def __init__(self, in_channels: int, head_dim: int = ATTN_HEAD_DIM) -> None:
         super().__init__()
         self.n_head = max(1, in_channels // head_dim)
@@ -59,6 +70,8 @@ class SelfAttention2d(_NativeOnly):  # blocks.py:51-72
 
 
 class FourierFeatures(_NativeOnly):  # blocks.py:78-87
+    """Random Fourier features of the noise level; a BUFFER (no gradient), consumed by `cond_embed_kernel`."""
+
     def __init__(self, cond_channels: int) -> None:
         super().__init__()
         assert cond_channels % 2 == 0
@@ -66,6 +79,9 @@ class FourierFeatures(_NativeOnly):  # blocks.py:78-87
 
 
 class Downsample(_NativeOnly):  # blocks.py:93-100
+    """3x3 stride-2 conv, orthogonal init.  Executed as the stride-1 tcgen05 conv stored at even (y, x) (exact for k = 3, p = 1);
+    backward-data through `zero_insert_prep_kernel` (the adjoint of the subsampling) + the transposed conv."""
+
     def __init__(self, in_channels: int) -> None:
         super().__init__()
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=1)
@@ -73,12 +89,18 @@ class Downsample(_NativeOnly):  # blocks.py:93-100
 
 
 class Upsample(_NativeOnly):  # blocks.py:103-110
+    """Nearest-2x upsample + 3x3 conv.  The upsample is addressing inside the operand pass (no upsampled tensor exists); its adjoint
+    in the backward pass is `sumpool2_kernel`."""
+
     def __init__(self, in_channels: int) -> None:
         super().__init__()
         self.conv = conv3x3(in_channels, in_channels)
 
 
 class SmallResBlock(_NativeOnly):  # blocks.py:116-123
+    """Actor-critic encoder block: skip(x) + conv3x3(silu(GroupNorm(x))); the 1x1 skip projection (when widths differ) runs split-fp16
+    so that the max-pool arg-max that follows matches the reference."""
+
     def __init__(self, in_channels: int, out_channels: int) -> None:
         super().__init__()
         self.f = nn.Sequential(GroupNorm(in_channels), nn.SiLU(inplace=True), conv3x3(in_channels, out_channels))
@@ -86,6 +108,10 @@ class SmallResBlock(_NativeOnly):  # blocks.py:116-123
 
 
 class ResBlock(_NativeOnly):  # blocks.py:129-147
+    """U-Net residual block.  Executed as: operand pass (AdaGN1 + SiLU [+ raw split-fp16 copy for proj]) -> conv1 -> operand pass
+    (AdaGN2 + SiLU) -> conv2 whose accumulator also receives the 1x1 skip projection as extra centre-tap K slabs (or the residual in
+    the epilogue when there is no projection) -> optional attention.  conv2 starts at zero like the reference (blocks.py:139)."""
+
     def __init__(self, in_channels: int, out_channels: int, cond_channels: int, attn: bool) -> None:
         super().__init__()
         self.proj = conv1x1(in_channels, out_channels) if in_channels != out_channels else nn.Identity()
@@ -98,6 +124,9 @@ class ResBlock(_NativeOnly):  # blocks.py:129-147
 
 
 class ResBlocks(_NativeOnly):  # blocks.py:153-177
+    """A level of the U-Net; in the up path every block reads cat(x, skip), which the conv consumes as TWO operand sources along K
+    (no concatenated tensor is materialised)."""
+
     def __init__(self, list_in_channels: List[int], list_out_channels: List[int], cond_channels: int, attn: bool) -> None:
         super().__init__()
         assert len(list_in_channels) == len(list_out_channels)
@@ -108,6 +137,10 @@ class ResBlocks(_NativeOnly):  # blocks.py:153-177
 
 
 class UNet(_NativeOnly):  # blocks.py:183-220 (constructor); forward lives in csrc/api.cu PlanBuilder::build
+    """Registration order (d_blocks, u_blocks reversed, mid_blocks, downsamples, upsamples) fixes the `state_dict` key order the native
+    executor indexes by (`Walker` in csrc/api.cu), so it must stay the reference's.  Pad / crop of `forward` (blocks.py:225-229,245) =
+    `resize_nhwc_kernel` around the level loop."""
+
     def __init__(self, cond_channels: int, depths: List[int], channels: List[int], attn_depths: List[int]) -> None:
         super().__init__()
         assert len(depths) == len(channels) == len(attn_depths)
