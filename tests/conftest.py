@@ -1,7 +1,13 @@
 import os
 import sys
 
-import pytest
+# The CPU oracle runs torch's OpenMP kernels.  With the default ACTIVE wait policy idle OpenMP threads spin, and on a host whose
+# cores are shared with other jobs that spinning collapses throughput (measured in the build container: the same six oracle
+# tests take 6 s alone, 136 s with three copies running side by side, 15 s with OMP_WAIT_POLICY=PASSIVE).  Must be set before
+# torch (libgomp) is loaded; a caller's own setting wins.
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
+import pytest  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
